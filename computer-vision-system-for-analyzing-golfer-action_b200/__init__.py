@@ -1,0 +1,19 @@
+"""golfer-b200: B200-native skeleton-sequence hot path (segment + align).
+
+Public surface (BASELINE.json north_star):
+    segment(skel[B,T,V,C]) -> logits[B,T,K]
+    align(a, b) -> (cost, path)
+Everything computes in hand-written sm_100a CUDA kernels behind the C ABI in
+include/golfer_b200.h; there is no CPU fallback.
+"""
+from . import config, params  # noqa: F401
+from .config import V0, V0_STRESS, GolfSegConfig  # noqa: F401
+from .host import (  # noqa: F401
+    GolferError,
+    Segmenter,
+    align,
+    compare,
+    library_path,
+    load_library,
+    segment,
+)

@@ -1,0 +1,371 @@
+"""Host-side mirror of the hot-path surface named in BASELINE.json's north_star:
+
+    segment(skel[B,T,V,C]) -> logits[B,T,K]
+    align(a, b)            -> (cost, path)
+
+The reference has no operator / plugin interface to mirror ("not
+in reference"; stages named at /root/reference/README.md:17-22, 27-34, 44-52),
+so these two calls ARE the interface.  Everything here is plumbing: ctypes over
+the C ABI of include/golfer_b200.h, with PyTorch used only for device memory and
+streams.  There is no CPU fallback: if the CUDA library is missing or no sm_100
+device is present these calls raise `GolferError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .config import V0, GolfSegConfig
+from .params import make_params, pack_blob
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libgolfer_b200.so"
+GS_MAX_BLOCKS = 8
+GS_MAX_BRANCHES = 8
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+# every symbol include/golfer_b200.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = (
+    "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
+    "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
+    "gs_compare", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
+)
+
+
+class GolferError(RuntimeError):
+    """Raised when the CUDA library is missing or a C-ABI call fails."""
+
+
+class _GsConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_joints", ctypes.c_int32), ("in_channels", ctypes.c_int32),
+        ("num_partitions", ctypes.c_int32), ("num_blocks", ctypes.c_int32),
+        ("widths", ctypes.c_int32 * GS_MAX_BLOCKS),
+        ("num_branches", ctypes.c_int32), ("kernel_size", ctypes.c_int32),
+        ("dilations", ctypes.c_int32 * GS_MAX_BRANCHES),
+        ("se_reduction", ctypes.c_int32), ("stj_reduction", ctypes.c_int32),
+        ("num_classes", ctypes.c_int32), ("precision", ctypes.c_int32),
+    ]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", _LIB_NAME)
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libgolfer_b200.so and declare the prototypes.  Fails loudly if the
+    extension has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            raise GolferError(
+                f"{path} is missing: the CUDA extension is not built and there is no CPU "
+                "fallback. Run __graft_entry__.build().")
+        try:
+            L = ctypes.CDLL(path)
+        except OSError as e:  # pragma: no cover
+            raise GolferError(f"cannot load {path}: {e}") from e
+        vp, i32, u8p = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+        L.gs_abi_version.restype = ctypes.c_int
+        L.gs_last_error.restype = ctypes.c_char_p
+        L.gs_create.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(_GsConfig), vp,
+                                ctypes.c_size_t, i32, i32]
+        L.gs_destroy.argtypes = [vp]
+        L.gs_segment.argtypes = [vp, vp, vp, u8p, i32, i32, vp]
+        L.gs_segment_host.argtypes = [vp, vp, vp, u8p, i32, i32]
+        L.gs_segment_features.argtypes = [vp, vp, i32, vp, i32, i32, vp]
+        L.gs_align.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.gs_align_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        L.gs_pair_cost.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.gs_compare.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.gs_launch_count.argtypes = [vp]
+        L.gs_launch_count.restype = ctypes.c_int64
+        L.gs_workspace_bytes.argtypes = [vp]
+        L.gs_workspace_bytes.restype = ctypes.c_size_t
+        L.gs_last_kernel_ms.argtypes = [vp]
+        L.gs_last_kernel_ms.restype = ctypes.c_float
+        for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
+                     "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
+                     "gs_compare"):
+            getattr(L, name).restype = ctypes.c_int
+        if L.gs_abi_version() != 1:
+            raise GolferError("libgolfer_b200.so ABI version mismatch")
+        _lib = L
+        return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().gs_last_error()
+        raise GolferError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _cfg_struct(cfg: GolfSegConfig, precision: str) -> _GsConfig:
+    if precision not in PRECISIONS:
+        raise GolferError(f"precision must be one of {sorted(PRECISIONS)}")
+    s = _GsConfig()
+    s.num_joints, s.in_channels = cfg.num_joints, cfg.in_channels
+    s.num_partitions, s.num_blocks = cfg.num_partitions, cfg.num_blocks
+    for i, w in enumerate(cfg.widths):
+        s.widths[i] = w
+    s.num_branches, s.kernel_size = cfg.num_branches, cfg.kernel_size
+    for i, d in enumerate(cfg.dilations):
+        s.dilations[i] = d
+    s.se_reduction, s.stj_reduction = cfg.se_reduction, cfg.stj_reduction
+    s.num_classes, s.precision = cfg.num_classes, PRECISIONS[precision]
+    return s
+
+
+def _stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """Owns one gs_ctx (weights + workspace on one device)."""
+
+    def __init__(self, device: int = 0, cfg: Optional[GolfSegConfig] = None,
+                 blob: Optional[np.ndarray] = None, precision: str = "bf16",
+                 max_B: int = 0, max_T: int = 0):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        self.device = int(device)
+        if cfg is None:
+            rc = self._L.gs_create(ctypes.byref(self._h), self.device, None, None, 0, 0, 0)
+        else:
+            blob = np.ascontiguousarray(blob, dtype=np.float32)
+            cs = _cfg_struct(cfg, precision)
+            rc = self._L.gs_create(ctypes.byref(self._h), self.device, ctypes.byref(cs),
+                                   blob.ctypes.data, blob.nbytes, int(max_B), int(max_T))
+        _check(rc, "gs_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self) -> int:
+        return int(self._L.gs_launch_count(self._h))
+
+    def workspace_bytes(self) -> int:
+        return int(self._L.gs_workspace_bytes(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._L.gs_last_kernel_ms(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.gs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Segmenter:
+    """segment(skel[B,T,V,C]) -> logits[B,T,K] on one B200.
+
+    CUDA tensor in -> CUDA tensor out (asynchronous on the current stream).
+    CPU tensor / ndarray in -> same kind out, through gs_segment_host (copies inside).
+    """
+
+    def __init__(self, cfg: GolfSegConfig = V0, params: Optional[Dict[str, np.ndarray]] = None,
+                 seed: int = 1234, precision: str = "bf16", device: int = 0,
+                 max_B: int = 256, max_T: int = 300):
+        self.cfg, self.precision = cfg, precision
+        self.params = params if params is not None else make_params(cfg, seed)
+        self.blob = pack_blob(cfg, self.params)
+        self.max_B, self.max_T = int(max_B), int(max_T)
+        self.ctx = Context(device, cfg, self.blob, precision, max_B, max_T)
+
+    # -- helpers -----------------------------------------------------------
+    def _shape(self, shape) -> Tuple[int, int]:
+        if len(shape) != 4 or shape[2] != self.cfg.num_joints or shape[3] != self.cfg.in_channels:
+            raise GolferError(
+                f"skel must be [B,T,{self.cfg.num_joints},{self.cfg.in_channels}], got {tuple(shape)}")
+        B, T = int(shape[0]), int(shape[1])
+        if B > self.max_B or T > self.max_T:
+            raise GolferError(f"B={B},T={T} exceeds the context's max_B={self.max_B},max_T={self.max_T}")
+        return B, T
+
+    def segment(self, skel, return_labels: bool = False):
+        torch = _torch()
+        L = self.ctx._L
+        K = self.cfg.num_classes
+        if isinstance(skel, torch.Tensor) and skel.is_cuda:
+            B, T = self._shape(skel.shape)
+            x = skel.contiguous().float()
+            logits = torch.empty((B, T, K), dtype=torch.float32, device=x.device)
+            labels = torch.empty((B, T), dtype=torch.uint8, device=x.device) if return_labels else None
+            if B and T:
+                _check(L.gs_segment(self.ctx.handle, x.data_ptr(), logits.data_ptr(),
+                                    labels.data_ptr() if return_labels else None, B, T,
+                                    _stream_ptr(torch)), "gs_segment")
+            return (logits, labels) if return_labels else logits
+        was_numpy = not isinstance(skel, torch.Tensor)
+        x = torch.as_tensor(np.asarray(skel) if was_numpy else skel, dtype=torch.float32).contiguous()
+        B, T = self._shape(x.shape)
+        logits = torch.empty((B, T, K), dtype=torch.float32, pin_memory=True)
+        labels = torch.empty((B, T), dtype=torch.uint8, pin_memory=True) if return_labels else None
+        if B and T:
+            _check(L.gs_segment_host(self.ctx.handle, x.data_ptr(), logits.data_ptr(),
+                                     labels.data_ptr() if return_labels else None, B, T),
+                   "gs_segment_host")
+        if was_numpy:
+            logits = logits.numpy()
+            labels = labels.numpy() if return_labels else None
+        return (logits, labels) if return_labels else logits
+
+    __call__ = segment
+
+    def features(self, skel, block: int):
+        """Block output after both attention gates, fp32 [B,T,V,C] (parity hook)."""
+        torch = _torch()
+        x = skel.contiguous().float()
+        B, T = self._shape(x.shape)
+        C = self.cfg.widths[block]
+        out = torch.empty((B, T, self.cfg.num_joints, C), dtype=torch.float32, device=x.device)
+        _check(self.ctx._L.gs_segment_features(self.ctx.handle, x.data_ptr(), int(block),
+                                               out.data_ptr(), B, T, _stream_ptr(torch)),
+               "gs_segment_features")
+        return out
+
+
+_default_segmenters: Dict[tuple, Segmenter] = {}
+_default_align_ctx: Dict[int, Context] = {}
+
+
+def _current_device(torch, t=None) -> int:
+    if t is not None and isinstance(t, torch.Tensor) and t.is_cuda:
+        return t.device.index
+    if not torch.cuda.is_available():
+        raise GolferError("no CUDA device: golfer_b200 has no CPU fallback")
+    return torch.cuda.current_device()
+
+
+def segment(skel, precision: str = "bf16", cfg: GolfSegConfig = V0, seed: int = 1234):
+    """Module-level convenience: seeded random-init weights (the reference ships none)."""
+    torch = _torch()
+    dev = _current_device(torch, skel)
+    B, T = int(skel.shape[0]), int(skel.shape[1])
+    key = (dev, precision, cfg.config_hash(), seed)
+    seg = _default_segmenters.get(key)
+    if seg is None or seg.max_B < B or seg.max_T < T:
+        if seg is not None:
+            seg.ctx.close()
+        seg = Segmenter(cfg, None, seed, precision, dev, max(B, 1), max(T, 1))
+        _default_segmenters[key] = seg
+    return seg.segment(skel)
+
+
+def _align_ctx(dev: int) -> Context:
+    ctx = _default_align_ctx.get(dev)
+    if ctx is None:
+        ctx = Context(dev)
+        _default_align_ctx[dev] = ctx
+    return ctx
+
+
+def align_batch(a, b, ctx: Optional[Context] = None, want_path: bool = True):
+    """a [N,Ta,V,Cc], b [N,Tb,V,Cc] -> (cost [N] f32, path [N,Ta+Tb-1,2] i32 (-1 padded), path_len [N] i32)."""
+    torch = _torch()
+    on_dev = isinstance(a, torch.Tensor) and a.is_cuda
+    if on_dev:
+        a = a.contiguous().float()
+        b = b.contiguous().float()
+    else:
+        was_numpy = not isinstance(a, torch.Tensor)
+        a = torch.as_tensor(np.asarray(a) if was_numpy else a, dtype=torch.float32).contiguous()
+        b = torch.as_tensor(np.asarray(b) if was_numpy else b, dtype=torch.float32).contiguous()
+    if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise GolferError(f"align expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
+    N, Ta, V, Cc = (int(s) for s in a.shape)
+    Tb = int(b.shape[1])
+    if Cc < 2:
+        raise GolferError("align needs at least (x, y) channels")
+    if Ta < 1 or Tb < 1:
+        raise GolferError("align needs at least one frame per sequence")
+    dev = _current_device(torch, a if on_dev else None)
+    ctx = ctx or _align_ctx(dev)
+    maxL = Ta + Tb - 1
+    kw = dict(device=a.device) if on_dev else dict(pin_memory=True)
+    cost = torch.empty((N,), dtype=torch.float32, **kw)
+    path = torch.empty((N, maxL, 2), dtype=torch.int32, **kw) if want_path else None
+    plen = torch.empty((N,), dtype=torch.int32, **kw) if want_path else None
+    if N:
+        if on_dev:
+            _check(ctx._L.gs_align(ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc,
+                                   cost.data_ptr(), path.data_ptr() if want_path else None,
+                                   plen.data_ptr() if want_path else None, _stream_ptr(torch)),
+                   "gs_align")
+        else:
+            _check(ctx._L.gs_align_host(ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc,
+                                        cost.data_ptr(), path.data_ptr() if want_path else None,
+                                        plen.data_ptr() if want_path else None), "gs_align_host")
+    return cost, path, plen
+
+
+def align(a, b):
+    """align(a, b) -> (cost, path).
+
+    One pair: a [Ta,V,Cc], b [Tb,V,Cc] -> (cost scalar tensor, path [L,2] int32).
+    Batch: a [N,Ta,V,Cc], b [N,Tb,V,Cc] -> (cost [N], path [N,Ta+Tb-1,2], rows past each
+    pair's length filled with -1)."""
+    torch = _torch()
+    single = (a.ndim == 3)
+    if single:
+        a, b = a[None], b[None]
+    cost, path, plen = align_batch(a, b)
+    if single:
+        n = int(plen[0])
+        return cost[0], path[0, :n]
+    return cost, path
+
+
+def pair_cost(a, b, ctx: Optional[Context] = None):
+    """Cost matrices only: a [N,Ta,V,Cc], b [N,Tb,V,Cc] (CUDA tensors) -> [N,Ta,Tb] fp32."""
+    torch = _torch()
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    N, Ta, V, Cc = (int(s) for s in a.shape)
+    Tb = int(b.shape[1])
+    ctx = ctx or _align_ctx(_current_device(torch, a))
+    out = torch.empty((N, Ta, Tb), dtype=torch.float32, device=a.device)
+    if N:
+        _check(ctx._L.gs_pair_cost(ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc,
+                                   out.data_ptr(), _stream_ptr(torch)), "gs_pair_cost")
+    return out
+
+
+def compare(a, b, path, path_len, ctx: Optional[Context] = None):
+    """"Compare 2 skeleton" (README.md:50-52): per aligned step, per joint distance.
+    a [N,Ta,V,Cc], b [N,Tb,V,Cc], path [N,Ta+Tb-1,2], path_len [N] (CUDA) -> [N,Ta+Tb-1,V] fp32."""
+    torch = _torch()
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    N, Ta, V, Cc = (int(s) for s in a.shape)
+    Tb = int(b.shape[1])
+    ctx = ctx or _align_ctx(_current_device(torch, a))
+    out = torch.empty((N, Ta + Tb - 1, V), dtype=torch.float32, device=a.device)
+    if N:
+        _check(ctx._L.gs_compare(ctx.handle, a.data_ptr(), b.data_ptr(), path.contiguous().data_ptr(),
+                                 path_len.contiguous().data_ptr(), N, Ta, Tb, V, Cc, out.data_ptr(),
+                                 _stream_ptr(torch)), "gs_compare")
+    return out

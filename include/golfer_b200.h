@@ -1,0 +1,145 @@
+/* golfer_b200.h — C ABI of libgolfer_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the skeleton-sequence hot path named by BASELINE.json's
+ * north_star:   segment(skel[B,T,V,C]) -> logits[B,T,K]
+ *               align(a, b)            -> (cost, path)
+ *
+ * Reference interface each entry point replaces: the reference ships no code,
+ * hence no plugin / operator / FFI interface exists to cite (SURVEY.md 8b:
+ * "not in reference").  The stages these functions implement are named at
+ *   /root/reference/README.md:17-18  action-segmentation model      -> gs_segment*
+ *   /root/reference/README.md:27-34  GCN / multi-branch TCN / channel / ST-joint attention
+ *   /root/reference/README.md:21-22  temporal-alignment model        -> gs_align*
+ *   /root/reference/README.md:44-49  alignment section
+ *   /root/reference/README.md:50-52  "Compare 2 skeleton"            -> gs_compare
+ * The signatures follow the ABI proposed in SURVEY.md 8b.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no C++ / torch types cross this boundary;
+ *   - every function returns 0 on success or a negative gs_status; it never throws;
+ *     gs_last_error() returns a thread-local message for the last failure;
+ *   - "dev" pointers are device memory on the context's device, "host" pointers are
+ *     host memory (pinned memory makes the host entry points asynchronous copies);
+ *   - the caller owns all input/output buffers; the library allocates its workspace
+ *     in gs_create (sized for max_B x max_T) and grows the alignment scratch only
+ *     when a larger (N,Ta,Tb) than ever seen arrives; steady state is allocation-free;
+ *   - device entry points are asynchronous on `cuda_stream` (a cudaStream_t passed as
+ *     void*) and never synchronise the host;
+ *   - one context per device; a context is not re-entrant; contexts are independent;
+ *   - there is NO CPU fallback: without a usable sm_100 device gs_create fails with
+ *     GS_ERR_NO_DEVICE.
+ */
+#ifndef GOLFER_B200_H
+#define GOLFER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+#define GS_MAX_BLOCKS 8
+#define GS_MAX_BRANCHES 8
+
+typedef enum gs_status {
+    GS_OK = 0,
+    GS_ERR_INVALID = -1,    /* bad argument / shape / config */
+    GS_ERR_NO_DEVICE = -2,  /* no CUDA device, or not compute capability 10.x */
+    GS_ERR_CUDA = -3,       /* a CUDA call failed (message has the CUDA error string) */
+    GS_ERR_NOMEM = -4,
+    GS_ERR_UNSUPPORTED = -5 /* valid request this build has no kernel for */
+} gs_status;
+
+typedef enum gs_precision {
+    GS_PREC_FP32 = 0, /* fp32 storage + fp32 CUDA-core math: the 1e-5 parity path */
+    GS_PREC_BF16 = 1  /* bf16 storage + tcgen05 (fp32 accumulate): the throughput path */
+} gs_precision;
+
+/* Mirrors golfer_b200.config.GolfSegConfig (frozen "v0" assumption set). */
+typedef struct gs_config {
+    int32_t num_joints;     /* V = 17 */
+    int32_t in_channels;    /* 3: x, y, confidence */
+    int32_t num_partitions; /* P = 3 */
+    int32_t num_blocks;
+    int32_t widths[GS_MAX_BLOCKS];
+    int32_t num_branches;   /* R */
+    int32_t kernel_size;    /* 3 */
+    int32_t dilations[GS_MAX_BRANCHES];
+    int32_t se_reduction;
+    int32_t stj_reduction;
+    int32_t num_classes;    /* K */
+    int32_t precision;      /* gs_precision */
+} gs_config;
+
+typedef struct gs_ctx gs_ctx;
+
+/* ABI version of the loaded library (compare with GS_ABI_VERSION). */
+int gs_abi_version(void);
+const char *gs_last_error(void);
+
+/* Create a context on `device`.  `cfg` + `weights_blob` (host memory; layout in
+ * params.py:pack_blob — header {magic,n_floats,n_blocks,0} then BN-folded fp32
+ * parameters) enable gs_segment*; pass cfg = NULL, weights_blob = NULL for an
+ * alignment-only context.  Workspace is sized for max_B clips of max_T frames. */
+int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weights_blob,
+              size_t weights_nbytes, int max_B, int max_T);
+int gs_destroy(gs_ctx *ctx);
+
+/* skel_dev [B,T,V,Cin] fp32 -> logits_dev [B,T,K] fp32 and, if non-NULL,
+ * labels_dev [B,T] u8 = first arg-max over K.  B <= max_B, T <= max_T. */
+int gs_segment(gs_ctx *ctx, const float *skel_dev, float *logits_dev, uint8_t *labels_dev,
+               int B, int T, void *cuda_stream);
+
+/* Same through HOST buffers: host->device copy of skel, the kernels, device->host
+ * copy of logits (and labels), chunked over clips so copies overlap compute;
+ * returns after the results are in host memory.  Either output may be NULL. */
+int gs_segment_host(gs_ctx *ctx, const float *skel_host, float *logits_host,
+                    uint8_t *labels_host, int B, int T);
+
+/* Debug / parity hook: run the network through block `block` (0-based) and write that
+ * block's output AFTER both attention gates as fp32 [B,T,V,C_block] to out_dev. */
+int gs_segment_features(gs_ctx *ctx, const float *skel_dev, int block, float *out_dev,
+                        int B, int T, void *cuda_stream);
+
+/* a_dev [N,Ta,V,Cc], b_dev [N,Tb,V,Cc] fp32 (Cc >= 2; channels 0,1 = x,y) ->
+ * cost_dev [N] fp32 = D[Ta-1][Tb-1]; path_dev [N, Ta+Tb-1, 2] int32 = (i,j) cells from
+ * (0,0) to (Ta-1,Tb-1), rows beyond path_len filled with -1; path_len_dev [N] int32.
+ * Arithmetic contract (bit-exact vs oracle/align.py): per-joint sqrt(dx*dx+dy*dy) with
+ * individually rounded IEEE fp32 ops (no FMA), joints summed in index order, divided
+ * by V; tie-break diagonal > up > left.  path_dev / path_len_dev may both be NULL
+ * (cost only). */
+int gs_align(gs_ctx *ctx, const float *a_dev, const float *b_dev, int N, int Ta, int Tb,
+             int V, int Cc, float *cost_dev, int32_t *path_dev, int32_t *path_len_dev,
+             void *cuda_stream);
+
+/* Same through HOST buffers (copies inside; returns when results are on the host). */
+int gs_align_host(gs_ctx *ctx, const float *a_host, const float *b_host, int N, int Ta,
+                  int Tb, int V, int Cc, float *cost_host, int32_t *path_host,
+                  int32_t *path_len_host);
+
+/* Materialise the pairwise cost matrices only: cost_matrix_dev [N,Ta,Tb] fp32
+ * (debug / parity hook for oracle/align.py:pair_cost). */
+int gs_pair_cost(gs_ctx *ctx, const float *a_dev, const float *b_dev, int N, int Ta, int Tb,
+                 int V, int Cc, float *cost_matrix_dev, void *cuda_stream);
+
+/* "Compare 2 skeleton" (README.md:50-52): per aligned step l < path_len[n], per joint v,
+ * out_dev[n,l,v] = sqrt(dx*dx+dy*dy) between a[n,path[l,0],v] and b[n,path[l,1],v];
+ * rows l >= path_len[n] are written as 0.  out_dev [N, Ta+Tb-1, V] fp32. */
+int gs_compare(gs_ctx *ctx, const float *a_dev, const float *b_dev, const int32_t *path_dev,
+               const int32_t *path_len_dev, int N, int Ta, int Tb, int V, int Cc,
+               float *out_dev, void *cuda_stream);
+
+/* Number of kernels this context has launched since creation (bench.py gpu_launches). */
+int64_t gs_launch_count(const gs_ctx *ctx);
+/* Bytes of device workspace currently held by the context. */
+size_t gs_workspace_bytes(const gs_ctx *ctx);
+/* CUDA-event time (ms) of the kernels of the most recent gs_segment / gs_align call,
+ * measured on its stream; blocks until that call has finished.  < 0 on error. */
+float gs_last_kernel_ms(gs_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLFER_B200_H */
