@@ -1,0 +1,496 @@
+// C ABI of libgolfer_b200.so (include/golfer_b200.h): context lifetime, weight blob
+// parsing, workspace, and the device / host entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr uint32_t kBlobMagic = 0x30575347u;  // "GSW0"
+
+template <typename T>
+int dmalloc(Ctx *ctx, T **p, size_t count) {
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+        return GS_ERR_NOMEM;
+    }
+    ctx->ws_bytes += bytes;
+    return GS_OK;
+}
+
+int validate_cfg(const gs_config *c) {
+    if (c->num_joints != 17 || c->num_partitions != 3 || c->kernel_size != 3) {
+        set_error("this build has kernels for V=17, P=3, 3-tap branches only");
+        return GS_ERR_UNSUPPORTED;
+    }
+    if (c->num_blocks < 1 || c->num_blocks > GS_MAX_BLOCKS || c->num_branches < 1 ||
+        c->num_branches > GS_MAX_BRANCHES || c->in_channels < 1 || c->num_classes < 1 ||
+        c->num_classes > 32 || c->se_reduction < 1 || c->stj_reduction < 1) {
+        set_error("gs_config out of range");
+        return GS_ERR_INVALID;
+    }
+    for (int i = 0; i < c->num_blocks; ++i) {
+        const int w = c->widths[i];
+        if (w < 1 || w > 1024 || w % c->num_branches || w % c->se_reduction || w % c->stj_reduction) {
+            set_error("width[%d]=%d invalid (<=1024, divisible by branches and reductions)", i, w);
+            return GS_ERR_INVALID;
+        }
+    }
+    for (int r = 0; r < c->num_branches; ++r)
+        if (c->dilations[r] < 1) {
+            set_error("dilation[%d] must be >= 1", r);
+            return GS_ERR_INVALID;
+        }
+    if (c->precision != GS_PREC_FP32 && c->precision != GS_PREC_BF16) {
+        set_error("unknown precision %d", c->precision);
+        return GS_ERR_INVALID;
+    }
+    return GS_OK;
+}
+
+// Walk the folded blob in params.py:fold_params order.
+int parse_blob(Ctx *ctx, const float *host, size_t nfloats) {
+    const gs_config &c = ctx->cfg;
+    const int V = c.num_joints, P = c.num_partitions, R = c.num_branches;
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        const float *p = ctx->d_blob + off;
+        off += n;
+        return p;
+    };
+    ctx->in_scale = take((size_t)V * c.in_channels);
+    ctx->in_shift = take((size_t)V * c.in_channels);
+    int cin = c.in_channels;
+    ctx->blocks.clear();
+    for (int i = 0; i < c.num_blocks; ++i) {
+        BlockParams b{};
+        b.cin = cin;
+        b.c = c.widths[i];
+        b.cr = b.c / R;
+        b.cs = b.c / c.se_reduction;
+        b.cj = b.c / c.stj_reduction;
+        b.has_res = (cin != b.c);
+        b.A = take((size_t)P * V * V);
+        b.Wg = take((size_t)P * cin * b.c);
+        b.bg = take(b.c);
+        b.W1 = take((size_t)b.c * b.c);
+        b.b1 = take(b.c);
+        b.W2 = take((size_t)R * 3 * b.cr * b.cr);
+        b.b2 = take(b.c);
+        if (b.has_res) {
+            b.Wr = take((size_t)cin * b.c);
+            b.br = take(b.c);
+        }
+        b.seW1 = take((size_t)b.c * b.cs);
+        b.seb1 = take(b.cs);
+        b.seW2 = take((size_t)b.cs * b.c);
+        b.seb2 = take(b.c);
+        b.jW = take((size_t)b.c * b.cj);
+        b.jb = take(b.cj);
+        b.jWt = take((size_t)b.cj * b.c);
+        b.jbt = take(b.c);
+        b.jWv = take((size_t)b.cj * b.c);
+        b.jbv = take(b.c);
+        ctx->blocks.push_back(b);
+        cin = b.c;
+    }
+    ctx->headW = take((size_t)cin * c.num_classes);
+    ctx->headb = take(c.num_classes);
+    if (off != nfloats) {
+        set_error("weight blob holds %zu floats, config needs %zu", nfloats, off);
+        return GS_ERR_INVALID;
+    }
+    (void)host;
+    return GS_OK;
+}
+
+int alloc_workspace(Ctx *ctx) {
+    const gs_config &c = ctx->cfg;
+    int cmax = c.in_channels;
+    for (int i = 0; i < c.num_blocks; ++i) cmax = cmax > c.widths[i] ? cmax : c.widths[i];
+    const size_t frames = (size_t)ctx->max_B * ctx->max_T;
+    const size_t rows = frames * c.num_joints;
+    const size_t esz = c.precision == GS_PREC_BF16 ? 2 : 4;
+    int rc;
+    auto bytes = [&](void **p, size_t n) { return dmalloc(ctx, (unsigned char **)p, n); };
+    if ((rc = bytes(&ctx->bufX, rows * cmax * esz))) return rc;
+    if ((rc = bytes(&ctx->bufXA, rows * cmax * 3 * esz))) return rc;
+    if ((rc = bytes(&ctx->bufY, rows * cmax * esz))) return rc;
+    if ((rc = bytes(&ctx->bufH, rows * cmax * esz))) return rc;
+    if ((rc = bytes(&ctx->bufR, rows * cmax * esz))) return rc;
+    if ((rc = bytes(&ctx->bufU[0], rows * cmax * esz))) return rc;
+    if ((rc = bytes(&ctx->bufU[1], rows * cmax * esz))) return rc;
+    const int nchunk = (ctx->max_T + 29) / 30;
+    if ((rc = dmalloc(ctx, &ctx->PT, frames * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->PV, (size_t)ctx->max_B * c.num_joints * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->PVpart, (size_t)ctx->max_B * nchunk * c.num_joints * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->seS, (size_t)ctx->max_B * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->gT, frames * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->gV, (size_t)ctx->max_B * c.num_joints * cmax))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_skel, rows * c.in_channels))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_logits, frames * c.num_classes))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_labels, frames))) return rc;
+    return GS_OK;
+}
+
+void free_ctx(Ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->bf16) bf16_path_destroy(ctx);
+    void *ptrs[] = {ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
+                    ctx->bufU[1], ctx->PT, ctx->PV, ctx->PVpart, ctx->seS, ctx->gT, ctx->gV, ctx->d_skel,
+                    ctx->d_logits, ctx->d_labels, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
+                    ctx->d_al_path, ctx->d_al_plen};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->own_stream[i]) cudaStreamDestroy(ctx->own_stream[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    delete ctx;
+}
+
+int forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T, int upto,
+            float *feat, cudaStream_t st) {
+    if (ctx->cfg.precision == GS_PREC_BF16)
+        return segment_bf16_forward(ctx, skel, logits, labels, B, T, upto, feat, st);
+    return segment_fp32_forward(ctx, skel, logits, labels, B, T, upto, feat, st);
+}
+
+int check_segment_args(Ctx *ctx, const void *in, int B, int T) {
+    if (!ctx || !ctx->has_net) {
+        set_error("context has no network (created without cfg/weights)");
+        return GS_ERR_INVALID;
+    }
+    if (!in || B < 1 || T < 1 || B > ctx->max_B || T > ctx->max_T) {
+        set_error("bad segment arguments: B=%d (max %d) T=%d (max %d)", B, ctx->max_B, T, ctx->max_T);
+        return GS_ERR_INVALID;
+    }
+    return GS_OK;
+}
+
+template <typename T>
+int grow(Ctx *ctx, T **p, size_t *cap, size_t count) {
+    if (count <= *cap) return GS_OK;
+    if (*p) {
+        cudaFree(*p);
+        ctx->ws_bytes -= *cap * sizeof(T);
+        *p = nullptr;
+        *cap = 0;
+    }
+    int rc = dmalloc(ctx, p, count);
+    if (rc == GS_OK) *cap = count;
+    return rc;
+}
+
+}  // namespace
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" {
+
+int gs_abi_version(void) { return GS_ABI_VERSION; }
+
+const char *gs_last_error(void) { return g_err; }
+
+int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weights_blob,
+              size_t weights_nbytes, int max_B, int max_T) {
+    if (!out) {
+        set_error("out is NULL");
+        return GS_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libgolfer_b200 has no CPU fallback");
+        return GS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range (%d visible)", device, ndev);
+        return GS_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    GS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                  prop.minor);
+        return GS_ERR_NO_DEVICE;
+    }
+    GS_CUDA(cudaSetDevice(device));
+    Ctx *ctx = new Ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc = GS_OK;
+    do {
+        for (int i = 0; i < 2; ++i) {
+            if (cudaStreamCreateWithFlags(&ctx->own_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("stream/event creation failed");
+                rc = GS_ERR_CUDA;
+                break;
+            }
+        }
+        if (rc) break;
+        if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+            set_error("event creation failed");
+            rc = GS_ERR_CUDA;
+            break;
+        }
+        if (!cfg) break;  // alignment-only context
+        if ((rc = validate_cfg(cfg))) break;
+        if (!weights_blob || weights_nbytes < 16 || max_B < 1 || max_T < 1) {
+            set_error("weights blob / max_B / max_T missing");
+            rc = GS_ERR_INVALID;
+            break;
+        }
+        ctx->cfg = *cfg;
+        ctx->max_B = max_B;
+        ctx->max_T = max_T;
+        const uint32_t *head = (const uint32_t *)weights_blob;
+        const size_t nfloats = head[1];
+        if (head[0] != kBlobMagic || (nfloats + 4) * 4 != weights_nbytes || (int)head[2] != cfg->num_blocks) {
+            set_error("weight blob header mismatch (magic %08x, n_floats %u, blocks %u, nbytes %zu)", head[0],
+                      head[1], head[2], weights_nbytes);
+            rc = GS_ERR_INVALID;
+            break;
+        }
+        if ((rc = dmalloc(ctx, &ctx->d_blob, nfloats))) break;
+        ctx->blob_floats = nfloats;
+        const float *body = (const float *)weights_blob + 4;
+        if (cudaMemcpy(ctx->d_blob, body, nfloats * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("weight upload failed");
+            rc = GS_ERR_CUDA;
+            break;
+        }
+        if ((rc = parse_blob(ctx, body, nfloats))) break;
+        if ((rc = alloc_workspace(ctx))) break;
+        ctx->has_net = true;
+        if (cfg->precision == GS_PREC_BF16 && (rc = bf16_path_create(ctx))) break;
+    } while (0);
+    if (rc != GS_OK) {
+        free_ctx(ctx);
+        return rc;
+    }
+    *out = (gs_ctx *)ctx;
+    return GS_OK;
+}
+
+int gs_destroy(gs_ctx *h) {
+    free_ctx((Ctx *)h);
+    return GS_OK;
+}
+
+int gs_segment(gs_ctx *h, const float *skel_dev, float *logits_dev, uint8_t *labels_dev, int B, int T,
+               void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_segment_args(ctx, skel_dev, B, T);
+    if (rc) return rc;
+    if (!logits_dev) {
+        set_error("logits_dev is NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    GS_CUDA(cudaEventRecord(ctx->ev_start, st));
+    rc = forward(ctx, skel_dev, logits_dev, labels_dev, B, T, -1, nullptr, st);
+    if (rc) return rc;
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
+    ctx->ev_valid = true;
+    return GS_OK;
+}
+
+int gs_segment_features(gs_ctx *h, const float *skel_dev, int block, float *out_dev, int B, int T,
+                        void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_segment_args(ctx, skel_dev, B, T);
+    if (rc) return rc;
+    if (!out_dev || block < 0 || block >= ctx->cfg.num_blocks) {
+        set_error("bad block index %d", block);
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return forward(ctx, skel_dev, nullptr, nullptr, B, T, block, out_dev, (cudaStream_t)cuda_stream);
+}
+
+int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8_t *labels_host, int B,
+                    int T) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_segment_args(ctx, skel_host, B, T);
+    if (rc) return rc;
+    GS_CUDA(cudaSetDevice(ctx->device));
+    const gs_config &c = ctx->cfg;
+    const size_t in_per = (size_t)T * c.num_joints * c.in_channels;
+    const size_t out_per = (size_t)T * c.num_classes;
+    // Clips are independent: split the batch in chunks; H2D of chunk i+1 (copy stream)
+    // overlaps the kernels of chunk i (compute stream); D2H follows each chunk.
+    const int nchunks = B >= 8 ? 4 : 1;
+    const int per = (B + nchunks - 1) / nchunks;
+    cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
+    GS_CUDA(cudaEventRecord(ctx->ev_start, sc));
+    for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+        const int nb = (B - b0) < per ? (B - b0) : per;
+        const int e = k & 1;
+        GS_CUDA(cudaMemcpyAsync(ctx->d_skel + b0 * in_per, skel_host + b0 * in_per, nb * in_per * 4,
+                                cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaEventRecord(ctx->ev_copy[e], sx));
+        GS_CUDA(cudaStreamWaitEvent(sc, ctx->ev_copy[e], 0));
+        // workspace is shared between chunks: kernels of chunk k run after chunk k-1 on `sc`
+        rc = forward(ctx, ctx->d_skel + b0 * in_per, ctx->d_logits + b0 * out_per,
+                     labels_host ? ctx->d_labels + (size_t)b0 * T : nullptr, nb, T, -1, nullptr, sc);
+        if (rc) return rc;
+        if (logits_host)
+            GS_CUDA(cudaMemcpyAsync(logits_host + b0 * out_per, ctx->d_logits + b0 * out_per, nb * out_per * 4,
+                                    cudaMemcpyDeviceToHost, sc));
+        if (labels_host)
+            GS_CUDA(cudaMemcpyAsync(labels_host + (size_t)b0 * T, ctx->d_labels + (size_t)b0 * T, (size_t)nb * T,
+                                    cudaMemcpyDeviceToHost, sc));
+    }
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, sc));
+    ctx->ev_valid = true;
+    GS_CUDA(cudaStreamSynchronize(sc));
+    return GS_OK;
+}
+
+static int check_align_args(Ctx *ctx, const void *a, const void *b, int N, int Ta, int Tb, int V, int Cc) {
+    if (!ctx || !a || !b || N < 1 || Ta < 1 || Tb < 1 || V < 1 || Cc < 2) {
+        set_error("bad align arguments: N=%d Ta=%d Tb=%d V=%d Cc=%d", N, Ta, Tb, V, Cc);
+        return GS_ERR_INVALID;
+    }
+    if ((long long)Ta + Tb - 1 > 65535) {
+        set_error("Ta+Tb-1 must be <= 65535");
+        return GS_ERR_UNSUPPORTED;
+    }
+    return GS_OK;
+}
+
+int gs_align(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, int Tb, int V, int Cc,
+             float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!cost_dev || ((path_dev == nullptr) != (path_len_dev == nullptr))) {
+        set_error("cost_dev must be set; path_dev and path_len_dev must both be set or both NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    GS_CUDA(cudaEventRecord(ctx->ev_start, st));
+    rc = align_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_dev, path_dev, path_len_dev, st);
+    if (rc) return rc;
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
+    ctx->ev_valid = true;
+    return GS_OK;
+}
+
+int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, int Ta, int Tb, int V, int Cc,
+                  float *cost_host, int32_t *path_host, int32_t *path_len_host) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_host, b_host, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!cost_host || ((path_host == nullptr) != (path_len_host == nullptr))) {
+        set_error("cost_host must be set; path_host and path_len_host must both be set or both NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    const size_t na = (size_t)N * Ta * V * Cc, nb = (size_t)N * Tb * V * Cc;
+    const size_t maxL = (size_t)Ta + Tb - 1;
+    if ((rc = grow(ctx, &ctx->d_al_a, &ctx->al_host_cap[0], na))) return rc;
+    if ((rc = grow(ctx, &ctx->d_al_b, &ctx->al_host_cap[1], nb))) return rc;
+    if ((rc = grow(ctx, &ctx->d_al_cost, &ctx->al_host_cap[2], (size_t)N))) return rc;
+    if (path_host) {
+        if ((rc = grow(ctx, &ctx->d_al_path, &ctx->al_host_cap[3], (size_t)N * maxL * 2))) return rc;
+        if ((rc = grow(ctx, &ctx->d_al_plen, &ctx->al_host_cap[4], (size_t)N))) return rc;
+    }
+    // Pairs are independent: chunk so the H2D of chunk k+1 overlaps the DTW of chunk k.
+    const int nchunks = N >= 64 ? 4 : 1;
+    const int per = (N + nchunks - 1) / nchunks;
+    cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
+    GS_CUDA(cudaEventRecord(ctx->ev_start, sc));
+    for (int k = 0, n0 = 0; n0 < N; ++k, n0 += per) {
+        const int cnt = (N - n0) < per ? (N - n0) : per;
+        const int e = k & 1;
+        const size_t oa = (size_t)n0 * Ta * V * Cc, ob = (size_t)n0 * Tb * V * Cc;
+        GS_CUDA(cudaMemcpyAsync(ctx->d_al_a + oa, a_host + oa, (size_t)cnt * Ta * V * Cc * 4,
+                                cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaMemcpyAsync(ctx->d_al_b + ob, b_host + ob, (size_t)cnt * Tb * V * Cc * 4,
+                                cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaEventRecord(ctx->ev_copy[e], sx));
+        GS_CUDA(cudaStreamWaitEvent(sc, ctx->ev_copy[e], 0));
+        rc = align_launch(ctx, ctx->d_al_a + oa, ctx->d_al_b + ob, cnt, Ta, Tb, V, Cc, ctx->d_al_cost + n0,
+                          path_host ? ctx->d_al_path + (size_t)n0 * maxL * 2 : nullptr,
+                          path_host ? ctx->d_al_plen + n0 : nullptr, sc);
+        if (rc) return rc;
+        GS_CUDA(cudaMemcpyAsync(cost_host + n0, ctx->d_al_cost + n0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sc));
+        if (path_host) {
+            GS_CUDA(cudaMemcpyAsync(path_host + (size_t)n0 * maxL * 2, ctx->d_al_path + (size_t)n0 * maxL * 2,
+                                    (size_t)cnt * maxL * 8, cudaMemcpyDeviceToHost, sc));
+            GS_CUDA(cudaMemcpyAsync(path_len_host + n0, ctx->d_al_plen + n0, (size_t)cnt * 4,
+                                    cudaMemcpyDeviceToHost, sc));
+        }
+    }
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, sc));
+    ctx->ev_valid = true;
+    GS_CUDA(cudaStreamSynchronize(sc));
+    return GS_OK;
+}
+
+int gs_pair_cost(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, int Tb, int V, int Cc,
+                 float *cost_matrix_dev, void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!cost_matrix_dev) {
+        set_error("cost_matrix_dev is NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return pair_cost_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_matrix_dev, (cudaStream_t)cuda_stream);
+}
+
+int gs_compare(gs_ctx *h, const float *a_dev, const float *b_dev, const int32_t *path_dev,
+               const int32_t *path_len_dev, int N, int Ta, int Tb, int V, int Cc, float *out_dev,
+               void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!path_dev || !path_len_dev || !out_dev) {
+        set_error("path / path_len / out is NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return compare_launch(ctx, a_dev, b_dev, path_dev, path_len_dev, N, Ta, Tb, V, Cc, out_dev,
+                          (cudaStream_t)cuda_stream);
+}
+
+int64_t gs_launch_count(const gs_ctx *h) { return h ? ((const Ctx *)h)->launches : -1; }
+
+size_t gs_workspace_bytes(const gs_ctx *h) { return h ? ((const Ctx *)h)->ws_bytes : 0; }
+
+float gs_last_kernel_ms(gs_ctx *h) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || !ctx->ev_valid) return -1.f;
+    if (cudaEventSynchronize(ctx->ev_stop) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Shared declarations for libgolfer_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/golfer_b200.h"
+
+namespace gs {
+
+void set_error(const char *fmt, ...);
+
+#define GS_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            gs::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GS_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define GS_KERNEL_CHECK()                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            gs::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GS_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- per-block folded parameters on the device (fp32 master copies) -------------
+struct BlockParams {
+    int cin, c, cr, cs, cj;
+    bool has_res;
+    const float *A;    // [P,V,V]
+    const float *Wg;   // [P*cin, c]
+    const float *bg;   // [c]
+    const float *W1;   // [c, c]
+    const float *b1;   // [c]
+    const float *W2;   // [R,3,cr,cr]
+    const float *b2;   // [c]
+    const float *Wr;   // [cin, c] or null
+    const float *br;
+    const float *seW1, *seb1, *seW2, *seb2;       // [c,cs] [cs] [cs,c] [c]
+    const float *jW, *jb, *jWt, *jbt, *jWv, *jbv; // [c,cj] [cj] [cj,c] [c] [cj,c] [c]
+};
+
+struct Bf16Path;   // segment_bf16.cu
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    bool has_net = false;
+    gs_config cfg{};
+    int max_B = 0, max_T = 0;
+    int64_t launches = 0;
+    size_t ws_bytes = 0;
+
+    // weights
+    float *d_blob = nullptr;      // whole folded blob (fp32)
+    size_t blob_floats = 0;
+    const float *in_scale = nullptr, *in_shift = nullptr, *headW = nullptr, *headb = nullptr;
+    std::vector<BlockParams> blocks;
+
+    // segmentation workspace (element type depends on precision)
+    void *bufX = nullptr;   // gated block input            [rows, Cmax]
+    void *bufXA = nullptr;  // adjacency-aggregated input   [rows, 3*Cmax]
+    void *bufY = nullptr;   // GCN output                   [rows, Cmax]
+    void *bufH = nullptr;   // branch 1x1 output            [rows, Cmax]
+    void *bufU[2] = {nullptr, nullptr};  // pre-attention block output, ping-pong
+    void *bufR = nullptr;   // residual projection          [rows, Cmax]
+    float *PT = nullptr;    // sum over joints  [B,T,Cmax]
+    float *PV = nullptr;    // sum over frames  [B,V,Cmax]
+    float *PVpart = nullptr;// per-chunk partials of PV
+    float *seS = nullptr;   // SE gate [B,Cmax]
+    float *gT = nullptr;    // s * a_t [B,T,Cmax]
+    float *gV = nullptr;    // a_v     [B,V,Cmax]
+    float *d_skel = nullptr;        // staging for the host entry points
+    float *d_logits = nullptr;
+    uint8_t *d_labels = nullptr;
+
+    // alignment scratch (grow-only)
+    void *align_ws = nullptr;
+    size_t align_ws_bytes = 0;
+    float *d_al_a = nullptr, *d_al_b = nullptr, *d_al_cost = nullptr;
+    int32_t *d_al_path = nullptr, *d_al_plen = nullptr;
+    size_t al_host_cap[5] = {0, 0, 0, 0, 0};
+
+    cudaStream_t own_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
+    bool ev_valid = false;
+
+    Bf16Path *bf16 = nullptr;
+};
+
+// align.cu
+int align_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
+                 float *cost, int32_t *path, int32_t *plen, cudaStream_t st);
+int pair_cost_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
+                     float *out, cudaStream_t st);
+int compare_launch(Ctx *ctx, const float *a, const float *b, const int32_t *path, const int32_t *plen,
+                   int N, int Ta, int Tb, int V, int Cc, float *out, cudaStream_t st);
+
+// segment_fp32.cu
+int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,
+                         int upto_block, float *feat_out, cudaStream_t st);
+// segment_bf16.cu
+int bf16_path_create(Ctx *ctx);
+void bf16_path_destroy(Ctx *ctx);
+int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,
+                         int upto_block, float *feat_out, cudaStream_t st);
+
+}  // namespace gs

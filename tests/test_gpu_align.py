@@ -1,0 +1,122 @@
+"""GPU parity for the alignment path, through the C ABI (bit-exact bar)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golfer_b200
+from oracle import align as oalign
+from oracle import align_native
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _check_against(a, b, cost, path, plen, ref_cost, ref_path, ref_plen):
+    assert np.array_equal(cost.cpu().numpy(), ref_cost)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+
+
+def test_golden_fixtures(golden_dir):
+    g = np.load(os.path.join(golden_dir, "align_small.npz"))
+    for tag in ("sq", "rect", "one"):
+        a, b = g[f"{tag}_a"], g[f"{tag}_b"]
+        cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+        _check_against(a, b, cost, path, plen, g[f"{tag}_cost"], g[f"{tag}_path"], g[f"{tag}_plen"])
+        cm = golfer_b200.host.pair_cost(_dev(a), _dev(b))
+        assert np.array_equal(cm.cpu().numpy(), g[f"{tag}_cm"])
+
+
+@pytest.mark.parametrize("N,Ta,Tb,Cc", [(5, 300, 300, 2), (4, 300, 257, 3), (3, 64, 300, 2), (2, 1, 1, 2),
+                                        (3, 1, 33, 2), (3, 33, 1, 2), (6, 17, 31, 2), (2, 500, 420, 2)])
+def test_matches_oracle_bitwise(N, Ta, Tb, Cc):
+    a, b = oalign.synth_swings(N, Ta, Tb, C=Cc, seed=Ta * 7 + Tb)
+    ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    _check_against(a, b, cost, path, plen, ref_cost, ref_path, ref_plen)
+
+
+def test_generic_kernel_path_large_and_odd_joint_count():
+    # Tb > 1024 and V != 17 both route to the generic (global-scratch) kernel
+    a, b = oalign.synth_swings(2, 40, 1100, seed=3)
+    rc, rp, rl = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    _check_against(a, b, cost, path, plen, rc, rp, rl)
+    a, b = oalign.synth_swings(3, 50, 45, V=25, seed=4)
+    rc, rp, rl = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    _check_against(a, b, cost, path, plen, rc, rp, rl)
+
+
+def test_self_alignment_zero_cost_diagonal():
+    a, _ = oalign.synth_swings(2, 300, 300, seed=9)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(a))
+    assert torch.all(cost == 0)
+    assert torch.all(plen == 300)
+    diag = torch.arange(300, dtype=torch.int32, device="cuda")
+    assert torch.equal(path[0, :300, 0], diag) and torch.equal(path[0, :300, 1], diag)
+    assert torch.all(path[:, 300:] == -1)
+
+
+def test_cost_only_mode_and_host_entry_point():
+    a, b = oalign.synth_swings(70, 120, 100, seed=21)
+    rc, rp, rl = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b), want_path=False)
+    assert path is None and np.array_equal(cost.cpu().numpy(), rc)
+    # host buffers in, host buffers out (H2D / D2H inside gs_align_host, chunked)
+    cost_h, path_h, plen_h = golfer_b200.host.align_batch(a, b)
+    assert not cost_h.is_cuda
+    assert np.array_equal(cost_h.numpy(), rc) and np.array_equal(path_h.numpy(), rp)
+    assert np.array_equal(plen_h.numpy(), rl)
+
+
+def test_public_align_signature_single_pair():
+    a, b = oalign.synth_swings(1, 30, 26, seed=2)
+    cost, path = golfer_b200.align(_dev(a[0]), _dev(b[0]))
+    c, p = oalign.align_ref(a[0], b[0])
+    assert cost.item() == c and np.array_equal(path.cpu().numpy(), p)
+
+
+def test_full_size_batch_properties_and_sampled_parity():
+    """BASELINE.json configs[2]: 4096 pairs of 300x300.  Whole batch vs the C oracle
+    (a few seconds on the host), plus size-independent path properties."""
+    N = 4096
+    a, b = oalign.synth_swings(N, 300, 300, seed=7)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    torch.cuda.synchronize()
+    rc, rp, rl = align_native.align_batch_c(a, b, os.cpu_count() or 1)
+    assert np.array_equal(cost.cpu().numpy(), rc)
+    assert np.array_equal(plen.cpu().numpy(), rl)
+    assert np.array_equal(path.cpu().numpy(), rp)
+    p = path.cpu().numpy()
+    L = plen.cpu().numpy()
+    assert np.all(p[:, 0] == 0) and np.all(L >= 300) and np.all(L <= 599)
+    for n in range(0, N, 257):
+        steps = np.diff(p[n, :L[n]], axis=0)
+        assert set(map(tuple, steps)) <= {(1, 1), (1, 0), (0, 1)}
+        assert tuple(p[n, L[n] - 1]) == (299, 299)
+
+
+def test_compare_two_skeletons():
+    a, b = oalign.synth_swings(3, 40, 36, seed=5)
+    da, db = _dev(a), _dev(b)
+    cost, path, plen = golfer_b200.host.align_batch(da, db)
+    out = golfer_b200.compare(da, db, path, plen).cpu().numpy()
+    for n in range(3):
+        L = int(plen[n])
+        ref = oalign.compare_ref(a[n], b[n], path[n, :L].cpu().numpy())
+        assert np.array_equal(out[n, :L], ref)
+        assert np.all(out[n, L:] == 0)
+
+
+def test_bad_arguments_raise():
+    a = torch.zeros(2, 8, 17, 2, device="cuda")
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.host.align_batch(a, torch.zeros(3, 8, 17, 2, device="cuda"))
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.host.align_batch(a[..., :1], a[..., :1])
