@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the golfer-b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): swing clips/s at T=300, V=17 (segmentation net, batch 256 per
+GPU, synthetic clips, random-init weights) plus DTW swing-pairs/s (4096 pairs of
+300x300 per GPU), each with its roofline fraction and the CPU oracle timed beside it.
+
+One "step" = one pass of `segment` over a batch of 256 clips per GPU (and, for the
+`align` object, one pass of `align` over 4096 pairs per GPU).  Ranks hold independent
+shards (weak scaling); for N>1 every step ends with the NCCL all-gather of logits
+(paths for align) that north_star names.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "swing clips/sec (T=300,V=17)"
+UNIT = "clips/s"
+T_FRAMES = 300
+BATCH = 256          # BASELINE.json configs[1]
+PAIRS = 4096         # BASELINE.json configs[2]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("GOLFER_PRECISION", "bf16"),
+                    choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--pairs", type=int, default=PAIRS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-align", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------ clocks ------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        busy = [x for x in sm if x > 0.5 * smax] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ inputs ------
+def synth_skel(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.randn(B, T, 17, 2, generator=g)
+    xy = xy - 0.5 * (xy[:, :, 11:12] + xy[:, :, 12:13])          # hip-centred
+    conf = torch.rand(B, T, 17, 1, generator=g)
+    return torch.cat([xy, conf], -1).contiguous()
+
+
+def synth_pairs(N, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.randn(N, 1, 17, 2, generator=g) + (torch.randn(N, T, 17, 2, generator=g) * 0.05).cumsum(1))
+    b = a[:, :1] + (torch.randn(N, 1, 17, 2, generator=g) * 0.1) + \
+        (torch.randn(N, T, 17, 2, generator=g) * 0.05).cumsum(1)
+    return a.contiguous(), b.contiguous()
+
+
+# ------------------------------------------------------------------ CPU arm -----
+_CPU_CACHE = {}
+
+
+def cpu_segment_rate(n_clips: int, threads: int, repeats: int = 1):
+    """Oracle (fp32 PyTorch, CPU) clips/s on a bounded sample of the same workload."""
+    import golfer_b200
+    from oracle import segnet
+    torch.set_num_threads(threads)
+    cfg = golfer_b200.V0
+    if "net" not in _CPU_CACHE:      # build the oracle once, outside every timed region
+        _CPU_CACHE["net"] = segnet.SegNet(cfg, golfer_b200.params.make_params(cfg, 1234))
+        _CPU_CACHE["x"] = synth_skel(16, T_FRAMES, 0)
+    net, x = _CPU_CACHE["net"], _CPU_CACHE["x"]
+    with torch.no_grad():
+        net(x[:1])
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            done = 0
+            while done < n_clips:           # chunks of <=16 clips bound the host memory
+                nb = min(16, n_clips - done)
+                net(x[:nb])
+                done += nb
+        dt = time.perf_counter() - t0
+    return n_clips * repeats / dt, dt
+
+
+def cpu_align_rate(n_pairs: int, threads: int):
+    from oracle import align_native
+    a, b = synth_pairs(n_pairs, T_FRAMES, 7)
+    a, b = a.numpy(), b.numpy()
+    align_native.align_batch_c(a[:2], b[:2], 1)
+    t0 = time.perf_counter()
+    align_native.align_batch_c(a, b, threads)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle (a port: the reference ships no code)
+    on all host cores, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    sample = 32
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_segment_rate(1, cores)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        cpu_segment_rate(sample, cores)
+        done += sample
+    dt = time.perf_counter() - t0
+    value = done / dt
+    al_rate, _ = cpu_align_rate(2048, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"segmentation net fwd, {sample} clips/step x {T_FRAMES} frames x 17 joints "
+                               "(bounded sample of configs[1]), CPU oracle"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} clips of T={T_FRAMES} in {dt:.1f}s, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "align": {"value": al_rate, "unit": "pairs/s", "sample": "2048 pairs 300x300, C oracle, all cores"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm -----
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import golfer_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    cfg = golfer_b200.V0
+    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    seg = golfer_b200.Segmenter(cfg, seed=1234, precision=args.precision, device=local, max_B=B,
+                                max_T=T_FRAMES)
+    skel_host = synth_skel(B, T_FRAMES, seed=rank).pin_memory()
+    skel = skel_host.to(dev)
+    gathered = torch.empty((world * B, T_FRAMES, cfg.num_classes), device=dev) if dist is not None else None
+
+    def seg_step():
+        logits = seg.segment(skel)
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, logits)
+        return logits
+
+    for _ in range(W):
+        seg_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    seg.ctx.profile_reset()
+    seg.ctx.profile(True)
+    l0 = seg.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        seg_step()
+    e1.record()
+    barrier()
+    seg.ctx.profile(False)
+    launches = seg.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    seg_ms = max_over_ranks(e0.elapsed_time(e1))
+    prof = seg.ctx.profile_read()
+    value = world * B * K / (seg_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (copies inside) ------
+    for _ in range(min(W, 2)):
+        seg.segment(skel_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out_host = seg.segment(skel_host)           # H2D + kernels + D2H, returns when done
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * B * K / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(skel_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)}
+
+    # ---- dominant kernel -> roofline --------------------------------------------
+    roofline = None
+    kernels = {}
+    if prof:
+        tot = sum(v["ms"] for v in prof.values())
+        for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            kernels[name] = {"share": round(v["ms"] / tot, 4), "ms_per_launch": v["ms"] / v["launches"],
+                             "launches_per_step": v["launches"] / K,
+                             "tflops": v["flops"] / v["ms"] / 1e9 if v["ms"] else 0.0,
+                             "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] else 0.0}
+        top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        tensor_bound = "gemm" in top or "tconv" in top
+        if tensor_bound:
+            ach = tv["flops"] / tv["ms"] / 1e9
+            peak = peaks["tf_sust"]
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": f"{peaks['source']} bf16 sustained"}
+        else:
+            ach = tv["bytes"] / tv["ms"] / 1e6
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['source']} copy"}
+    whole_net = {
+        "tflops": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 * world / world,
+        "frac_of_tensor_peak": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 / peaks["tf_sust"],
+        "compulsory_gbs": cfg.compulsory_bytes_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e9,
+        "frac_of_hbm_peak": cfg.compulsory_bytes_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e9 / peaks["hbm"],
+    }
+
+    # ---- alignment: 4096 pairs of 300x300 per GPU ------------------------------------
+    align_obj = None
+    if not args.no_align:
+        N = args.pairs
+        a_host, b_host = synth_pairs(N, T_FRAMES, seed=7 + rank)
+        a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
+        a, b = a_host.to(dev), b_host.to(dev)
+        actx = golfer_b200.host.Context(local)
+        maxL = 2 * T_FRAMES - 1
+        gpath = torch.empty((world * N, maxL, 2), dtype=torch.int32, device=dev) if dist is not None else None
+
+        def al_step():
+            cost, path, plen = golfer_b200.host.align_batch(a, b, ctx=actx)
+            if dist is not None:
+                dist.all_gather_into_tensor(gpath, path)
+            return cost
+
+        for _ in range(W):
+            al_step()
+        barrier()
+        actx.profile_reset()
+        actx.profile(True)
+        al0 = actx.launch_count()
+        e0.record()
+        for _ in range(K):
+            al_step()
+        e1.record()
+        barrier()
+        actx.profile(False)
+        launches += actx.launch_count() - al0
+        al_ms = max_over_ranks(e0.elapsed_time(e1))
+        aprof = actx.profile_read().get("dtw_wavefront")
+        t0 = time.perf_counter()
+        for _ in range(K):
+            golfer_b200.host.align_batch(a_host, b_host, ctx=actx)
+        torch.cuda.synchronize()
+        al_e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        pairs_s = world * N * K / (al_ms * 1e-3)
+        ach = aprof["bytes"] / aprof["ms"] / 1e6 if aprof else None
+        align_obj = {
+            "metric": "DTW swing pairs/sec (300x300, V=17)", "value": pairs_s, "unit": "pairs/s",
+            "ms_per_step": al_ms / K, "pairs_per_step_per_gpu": N,
+            "e2e": {"value": world * N * K / al_e2e_s, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(a_host.numel() * 4 * 2),
+                    "d2h_bytes_per_step": int(N * (maxL * 8 + 8))},
+            "roofline": {"kernel": "dtw_wavefront", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
+                         "note": "compulsory bytes 86,396 B/pair; the binding limit is fp32 issue/sqrt "
+                                 "throughput (~1.5-3 M pairs/s per GPU), not HBM (SURVEY.md 7 item 4)",
+                         "instr_bound_pairs_per_s_per_gpu": 1.5e6},
+        }
+
+    # ---- CPU oracle timed beside it (rank 0, N=1 only; bounded sample) ---------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        rate, dt = cpu_segment_rate(128, cores)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"128 clips of T={T_FRAMES} (half of the 256-clip batch) in {dt:.1f}s, "
+                                  f"oracle/segnet.py fp32 on torch CPU, {cores} threads"}
+        if align_obj is not None:
+            ar, adt = cpu_align_rate(2048, cores)
+            align_obj["cpu_baseline"] = {"value": ar, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                         "sample": f"2048 pairs 300x300 in {adt:.1f}s, oracle/align_c.c OpenMP"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": seg_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"segmentation net fwd (GolfSegConfig {cfg.version} {cfg.config_hash()}), "
+                                   f"{B} clips/GPU x {T_FRAMES} frames x 17 joints x 3 ch (BASELINE configs[1])",
+                       "global_batch": world * B, "frames": T_FRAMES, "parallelism": f"dp{world}",
+                       "l2_policy": "per-step working set (activations, several hundred MB) exceeds the 126 MB L2",
+                       "collective": "all_gather(logits) inside each step" if world > 1 else "none"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "whole_net": whole_net, "kernels": kernels, "cpu_baseline": cpu_baseline, "align": align_obj,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,14 @@ namespace gs {
 
 static thread_local char g_err[512] = "";
 
+const char *kernel_name(int id) {
+    static const char *names[K_COUNT] = {
+        "aggregate_fp32", "gemm_gcn_fp32", "gemm_tcn1x1_fp32", "gemm_res_fp32", "tconv_fp32", "stats", "se_gate",
+        "stj_gate", "head", "features", "dtw_wavefront", "dtw_generic", "pair_cost", "compare",
+        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc"};
+    return (id >= 0 && id < K_COUNT) ? names[id] : "?";
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -160,6 +168,10 @@ void free_ctx(Ctx *ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->own_stream[i]) cudaStreamDestroy(ctx->own_stream[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    }
+    for (ProfSlot &ps : ctx->prof.pool) {
+        cudaEventDestroy(ps.e0);
+        cudaEventDestroy(ps.e1);
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -478,6 +490,46 @@ int gs_compare(gs_ctx *h, const float *a_dev, const float *b_dev, const int32_t 
     GS_CUDA(cudaSetDevice(ctx->device));
     return compare_launch(ctx, a_dev, b_dev, path_dev, path_len_dev, N, Ta, Tb, V, Cc, out_dev,
                           (cudaStream_t)cuda_stream);
+}
+
+int gs_profile_enable(gs_ctx *h, int on) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx) return GS_ERR_INVALID;
+    ctx->prof.on = on != 0;
+    return GS_OK;
+}
+
+int gs_profile_reset(gs_ctx *h) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx) return GS_ERR_INVALID;
+    Profiler &p = ctx->prof;
+    p.used = 0;
+    for (int i = 0; i < K_COUNT; ++i) p.ms[i] = p.flops[i] = p.bytes[i] = 0, p.launches[i] = 0;
+    return GS_OK;
+}
+
+int gs_profile_kernels(void) { return K_COUNT; }
+
+int gs_profile_read(gs_ctx *h, int kernel, const char **name, double *total_ms, int64_t *launches,
+                    double *alg_flops, double *alg_bytes) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || kernel < 0 || kernel >= K_COUNT) return GS_ERR_INVALID;
+    Profiler &p = ctx->prof;
+    if (p.used) {   // fold the recorded event pairs into the per-kernel totals
+        GS_CUDA(cudaSetDevice(ctx->device));
+        GS_CUDA(cudaDeviceSynchronize());
+        for (size_t i = 0; i < p.used; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.pool[i].e0, p.pool[i].e1) == cudaSuccess) p.ms[p.pool[i].id] += ms;
+        }
+        p.used = 0;
+    }
+    if (name) *name = kernel_name(kernel);
+    if (total_ms) *total_ms = p.ms[kernel];
+    if (launches) *launches = p.launches[kernel];
+    if (alg_flops) *alg_flops = p.flops[kernel];
+    if (alg_bytes) *alg_bytes = p.bytes[kernel];
+    return GS_OK;
 }
 
 int64_t gs_launch_count(const gs_ctx *h) { return h ? ((const Ctx *)h)->launches : -1; }

@@ -52,6 +52,30 @@ struct BlockParams {
 
 struct Bf16Path;   // segment_bf16.cu
 
+// ---- per-kernel profiling (bench.py roofline): CUDA events around each launch ----
+enum KernelId {
+    K_AGG = 0, K_GEMM_GCN, K_GEMM_TCN1, K_GEMM_RES, K_TCONV, K_STATS, K_SE, K_STJ, K_HEAD, K_FEAT,
+    K_DTW, K_DTW_GENERIC, K_PAIRCOST, K_COMPARE,
+    K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC,
+    K_COUNT
+};
+const char *kernel_name(int id);
+
+struct ProfSlot {
+    cudaEvent_t e0, e1;
+    int id;
+};
+
+struct Profiler {
+    bool on = false;
+    std::vector<ProfSlot> pool;
+    size_t used = 0;
+    double ms[K_COUNT] = {0};
+    double flops[K_COUNT] = {0};
+    double bytes[K_COUNT] = {0};
+    int64_t launches[K_COUNT] = {0};
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
@@ -96,6 +120,35 @@ struct Ctx {
     bool ev_valid = false;
 
     Bf16Path *bf16 = nullptr;
+    Profiler prof;
+};
+
+// Brackets ONE kernel launch: counts it, and when profiling is on records a CUDA event
+// pair on the launch stream plus the launch's algorithmic flops / bytes.
+struct LaunchScope {
+    Ctx *c;
+    int slot = -1;
+    cudaStream_t st;
+    LaunchScope(Ctx *ctx, int id, cudaStream_t s, double flops = 0, double bytes = 0) : c(ctx), st(s) {
+        c->launches += 1;
+        Profiler &p = c->prof;
+        if (!p.on) return;
+        p.launches[id] += 1;
+        p.flops[id] += flops;
+        p.bytes[id] += bytes;
+        if (p.used == p.pool.size()) {
+            if (p.pool.size() >= 32768) return;
+            ProfSlot ns{};
+            if (cudaEventCreate(&ns.e0) != cudaSuccess || cudaEventCreate(&ns.e1) != cudaSuccess) return;
+            p.pool.push_back(ns);
+        }
+        slot = (int)p.used++;
+        p.pool[slot].id = id;
+        cudaEventRecord(p.pool[slot].e0, st);
+    }
+    ~LaunchScope() {
+        if (slot >= 0) cudaEventRecord(c->prof.pool[slot].e1, st);
+    }
 };
 
 // align.cu

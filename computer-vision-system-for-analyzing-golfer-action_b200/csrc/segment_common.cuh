@@ -206,24 +206,33 @@ int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T,
     const int nchunk = cdiv(T, kStatChunk);
     {
         dim3 grid(nchunk, B, cdiv(C, 128));
-        stats_kernel<TU, V><<<grid, 128, 0, st>>>(U, T, C, ctx->PT, ctx->PVpart);
+        {
+            LaunchScope ls(ctx, K_STATS, st, 2.0 * B * T * V * C, (double)B * T * V * C * sizeof(TU));
+            stats_kernel<TU, V><<<grid, 128, 0, st>>>(U, T, C, ctx->PT, ctx->PVpart);
+        }
         GS_KERNEL_CHECK();
     }
     {
         const int threads = ((C + 31) / 32) * 32;
-        se_kernel<V><<<B, threads, (C + bp.cs) * sizeof(float), st>>>(
-            ctx->PT, ctx->PVpart, T, C, bp.cs, nchunk, bp.seW1, bp.seb1, bp.seW2, bp.seb2, ctx->seS, ctx->PV);
+        {
+            LaunchScope ls(ctx, K_SE, st, 4.0 * B * C * bp.cs, (double)B * T * C * 4);
+            se_kernel<V><<<B, threads, (C + bp.cs) * sizeof(float), st>>>(
+                ctx->PT, ctx->PVpart, T, C, bp.cs, nchunk, bp.seW1, bp.seb1, bp.seW2, bp.seb2, ctx->seS,
+                ctx->PV);
+        }
         GS_KERNEL_CHECK();
     }
     {
         const int threads = ((C + 31) / 32) * 32;
         dim3 grid(cdiv(T + V, kStjPos), B);
-        stj_kernel<V><<<grid, threads, kStjPos * (C + bp.cj) * sizeof(float), st>>>(
-            ctx->PT, ctx->PV, ctx->seS, T, C, bp.cj, bp.jW, bp.jb, bp.jWt, bp.jbt, bp.jWv, bp.jbv, ctx->gT,
-            ctx->gV);
+        {
+            LaunchScope ls(ctx, K_STJ, st, 4.0 * B * (T + V) * C * bp.cj, 2.0 * B * (T + V) * C * 4);
+            stj_kernel<V><<<grid, threads, kStjPos * (C + bp.cj) * sizeof(float), st>>>(
+                ctx->PT, ctx->PV, ctx->seS, T, C, bp.cj, bp.jW, bp.jb, bp.jWt, bp.jbt, bp.jWv, bp.jbv, ctx->gT,
+                ctx->gV);
+        }
         GS_KERNEL_CHECK();
     }
-    ctx->launches += 3;
     return GS_OK;
 }
 
@@ -232,10 +241,12 @@ int launch_head(Ctx *ctx, const TU *U, int B, int T, int C, float *logits, uint8
     constexpr int V = 17;
     const int K = ctx->cfg.num_classes;
     const int threads = ((C + 31) / 32) * 32;
-    head_kernel<TU, V><<<B * T, threads, (threads / 32) * K * sizeof(float), st>>>(
-        U, ctx->gT, ctx->gV, T, C, K, ctx->headW, ctx->headb, logits, labels);
+    {
+        LaunchScope ls(ctx, K_HEAD, st, 2.0 * B * T * C * (V + K), (double)B * T * V * C * sizeof(TU));
+        head_kernel<TU, V><<<B * T, threads, (threads / 32) * K * sizeof(float), st>>>(
+            U, ctx->gT, ctx->gV, T, C, K, ctx->headW, ctx->headb, logits, labels);
+    }
     GS_KERNEL_CHECK();
-    ctx->launches += 1;
     return GS_OK;
 }
 
@@ -244,9 +255,11 @@ int launch_features(Ctx *ctx, const TU *U, int B, int T, int C, float *out, cuda
     const size_t total = (size_t)B * T * 17 * C;
     int grid = (int)((total + 255) / 256 < (size_t)ctx->sm_count * 16 ? (total + 255) / 256
                                                                        : (size_t)ctx->sm_count * 16);
-    features_kernel<TU><<<grid, 256, 0, st>>>(U, ctx->gT, ctx->gV, T, 17, C, total, out);
+    {
+        LaunchScope ls(ctx, K_FEAT, st);
+        features_kernel<TU><<<grid, 256, 0, st>>>(U, ctx->gT, ctx->gV, T, 17, C, total, out);
+    }
     GS_KERNEL_CHECK();
-    ctx->launches += 1;
     return GS_OK;
 }
 

@@ -157,12 +157,14 @@ int grid_for(const Ctx *ctx, size_t total, int threads) {
 }
 
 template <bool RELU>
-int launch_gemm(Ctx *ctx, const float *In, const float *W, const float *bias, float *Out, size_t M, int N,
-                int K, cudaStream_t st) {
+int launch_gemm(Ctx *ctx, int kid, const float *In, const float *W, const float *bias, float *Out, size_t M,
+                int N, int K, cudaStream_t st) {
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-    gemm_rows_kernel<RELU><<<grid, 256, 0, st>>>(In, W, bias, Out, M, N, K);
+    {
+        LaunchScope ls(ctx, kid, st, 2.0 * M * N * K, 4.0 * M * (N + K));
+        gemm_rows_kernel<RELU><<<grid, 256, 0, st>>>(In, W, bias, Out, M, N, K);
+    }
     GS_KERNEL_CHECK();
-    ctx->launches += 1;
     return GS_OK;
 }
 
@@ -184,27 +186,31 @@ int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         const BlockParams &bp = ctx->blocks[i];
         float *U = (float *)ctx->bufU[i & 1];
         const size_t items = nframes * bp.cin;
-        if (i == 0) {
-            aggregate_kernel<float, float, 3><<<grid_for(ctx, items, 256), 256, 0, st>>>(
-                skel, nullptr, nullptr, ctx->in_scale, ctx->in_shift, bp.A, T, bp.cin, nframes, X, XA);
-        } else {
-            aggregate_kernel<float, float, 3><<<grid_for(ctx, items, 256), 256, 0, st>>>(
-                Uprev, ctx->gT, ctx->gV, nullptr, nullptr, bp.A, T, bp.cin, nframes, X, XA);
+        {
+            LaunchScope ls(ctx, K_AGG, st, 2.0 * rows * V17 * 3 * bp.cin, 4.0 * rows * bp.cin * 5);
+            if (i == 0) {
+                aggregate_kernel<float, float, 3><<<grid_for(ctx, items, 256), 256, 0, st>>>(
+                    skel, nullptr, nullptr, ctx->in_scale, ctx->in_shift, bp.A, T, bp.cin, nframes, X, XA);
+            } else {
+                aggregate_kernel<float, float, 3><<<grid_for(ctx, items, 256), 256, 0, st>>>(
+                    Uprev, ctx->gT, ctx->gV, nullptr, nullptr, bp.A, T, bp.cin, nframes, X, XA);
+            }
         }
         GS_KERNEL_CHECK();
-        ctx->launches += 1;
-        if ((rc = launch_gemm<true>(ctx, XA, bp.Wg, bp.bg, Y, rows, bp.c, 3 * bp.cin, st))) return rc;
-        if ((rc = launch_gemm<true>(ctx, Y, bp.W1, bp.b1, H, rows, bp.c, bp.c, st))) return rc;
+        if ((rc = launch_gemm<true>(ctx, K_GEMM_GCN, XA, bp.Wg, bp.bg, Y, rows, bp.c, 3 * bp.cin, st))) return rc;
+        if ((rc = launch_gemm<true>(ctx, K_GEMM_TCN1, Y, bp.W1, bp.b1, H, rows, bp.c, bp.c, st))) return rc;
         const float *res = X;
         if (bp.has_res) {
-            if ((rc = launch_gemm<false>(ctx, X, bp.Wr, bp.br, R, rows, bp.c, bp.cin, st))) return rc;
+            if ((rc = launch_gemm<false>(ctx, K_GEMM_RES, X, bp.Wr, bp.br, R, rows, bp.c, bp.cin, st))) return rc;
             res = R;
         }
         const size_t total = rows * bp.c;
-        tconv_kernel<<<grid_for(ctx, total, 256), 256, 0, st>>>(H, res, bp.W2, bp.b2, U, T, bp.c, bp.cr, dil,
-                                                                total);
+        {
+            LaunchScope ls(ctx, K_TCONV, st, 2.0 * total * 3 * bp.cr, 4.0 * total * 3);
+            tconv_kernel<<<grid_for(ctx, total, 256), 256, 0, st>>>(H, res, bp.W2, bp.b2, U, T, bp.c, bp.cr, dil,
+                                                                    total);
+        }
         GS_KERNEL_CHECK();
-        ctx->launches += 1;
         if ((rc = launch_attention<float>(ctx, bp, U, B, T, st))) return rc;
         Uprev = U;
     }

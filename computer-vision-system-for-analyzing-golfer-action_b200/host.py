@@ -33,6 +33,7 @@ ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
     "gs_compare", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
+    "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read",
 )
 
 
@@ -95,6 +96,14 @@ def load_library():
         L.gs_workspace_bytes.restype = ctypes.c_size_t
         L.gs_last_kernel_ms.argtypes = [vp]
         L.gs_last_kernel_ms.restype = ctypes.c_float
+        L.gs_profile_enable.argtypes = [vp, i32]
+        L.gs_profile_reset.argtypes = [vp]
+        L.gs_profile_kernels.restype = ctypes.c_int
+        L.gs_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        for name in ("gs_profile_enable", "gs_profile_reset", "gs_profile_read"):
+            getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
                      "gs_compare"):
@@ -166,6 +175,25 @@ class Context:
 
     def last_kernel_ms(self) -> float:
         return float(self._L.gs_last_kernel_ms(self._h))
+
+    def profile(self, on: bool):
+        _check(self._L.gs_profile_enable(self._h, 1 if on else 0), "gs_profile_enable")
+
+    def profile_reset(self):
+        _check(self._L.gs_profile_reset(self._h), "gs_profile_reset")
+
+    def profile_read(self):
+        """{kernel name: dict(ms, launches, flops, bytes)} for kernels launched while profiling."""
+        out = {}
+        for k in range(self._L.gs_profile_kernels()):
+            name = ctypes.c_char_p()
+            ms, fl, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+            n = ctypes.c_int64()
+            _check(self._L.gs_profile_read(self._h, k, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(n),
+                                           ctypes.byref(fl), ctypes.byref(by)), "gs_profile_read")
+            if n.value:
+                out[name.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+        return out
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

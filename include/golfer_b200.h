@@ -131,6 +131,17 @@ int gs_compare(gs_ctx *ctx, const float *a_dev, const float *b_dev, const int32_
                const int32_t *path_len_dev, int N, int Ta, int Tb, int V, int Cc,
                float *out_dev, void *cuda_stream);
 
+/* Per-kernel profiling for the roofline report: while enabled, every kernel launch is
+ * bracketed by a CUDA event pair on its stream.  gs_profile_read synchronises the device,
+ * folds the pending event pairs, and returns for kernel index `kernel`
+ * (0 <= kernel < gs_profile_kernels()) its name, summed device time, launch count and
+ * the summed ALGORITHMIC flops / bytes of those launches (un-padded). */
+int gs_profile_enable(gs_ctx *ctx, int on);
+int gs_profile_reset(gs_ctx *ctx);
+int gs_profile_kernels(void);
+int gs_profile_read(gs_ctx *ctx, int kernel, const char **name, double *total_ms,
+                    int64_t *launches, double *alg_flops, double *alg_bytes);
+
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 int64_t gs_launch_count(const gs_ctx *ctx);
 /* Bytes of device workspace currently held by the context. */
