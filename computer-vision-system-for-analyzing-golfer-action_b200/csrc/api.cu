@@ -292,6 +292,7 @@ int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weight
             rc = GS_ERR_CUDA;
             break;
         }
+        ctx->h_blob.assign(body, body + nfloats);
         if ((rc = parse_blob(ctx, body, nfloats))) break;
         if ((rc = alloc_workspace(ctx))) break;
         ctx->has_net = true;

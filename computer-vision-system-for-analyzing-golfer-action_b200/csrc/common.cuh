@@ -87,6 +87,7 @@ struct Ctx {
 
     // weights
     float *d_blob = nullptr;      // whole folded blob (fp32)
+    std::vector<float> h_blob;    // host copy (bf16 path repacks weights from it)
     size_t blob_floats = 0;
     const float *in_scale = nullptr, *in_shift = nullptr, *headW = nullptr, *headb = nullptr;
     std::vector<BlockParams> blocks;

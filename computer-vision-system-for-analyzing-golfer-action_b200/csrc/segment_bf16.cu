@@ -1,18 +1,338 @@
-// bf16 throughput path (tcgen05 / TMA) — placeholder until the kernels land.
+// bf16 throughput path of the segmentation network: bf16 activations in HBM, every dense
+// contraction on tcgen05 tensor cores (tc_gemm.cuh) with fp32 accumulation in TMEM.
+//
+// Per block i >= 1 (block 0 has Cin = 3 and runs its tiny K=9 / K=3 contractions in
+// `front_kernel` on CUDA cores):
+//   aggregate   U_{i-1} * gates -> Xg [rows,Cin], XA [rows,3Cin]            (CUDA cores, fp32 math)
+//   tc_gemm     Y = relu(XA . Wg + bg)                                       (K = 3Cin, N = C)
+//   tc_gemm     H = relu(Y . W1 + b1)                                        (K = C,    N = C)
+//   tc_gemm     U = relu(sum_{r,j} shift_{(j-1)d_r}(H_r) . W2[r,j] + Xg . Wr + b)   (taps + residual)
+//   stats / se / stj (segment_common.cuh)                                    -> gates for block i+1
+// Rounding points (mirrored by oracle/segnet_bf16.py): weights, Xg, XA, Y, H, U (and block 0's
+// residual projection) are rounded to bf16; everything else is fp32.
+//
+// Stages replaced: /root/reference/README.md:27-34.
 #include "segment_common.cuh"
+#include "tc_gemm.cuh"
 
 namespace gs {
 
-int bf16_path_create(Ctx *ctx) {
-    (void)ctx;
+struct BlockMaps {
+    CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
+    CUtensorMap wg, w1, w2, wr;
+};
+
+struct Bf16Path {
+    std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
+    std::vector<float *> bias_t;                        // b2 (+ br)
+    std::vector<BlockMaps> maps;
+    int maps_T = -1;
+};
+
+namespace {
+
+// ---- block 0 on CUDA cores: input BN + adjacency + K=9 mix (+ReLU) and K=3 residual ------
+constexpr int kFrontFrames = 8;
+
+__global__ void __launch_bounds__(256)
+front_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale, const float *__restrict__ in_shift,
+             const float *__restrict__ A, const float *__restrict__ Wg, const float *__restrict__ bg,
+             const float *__restrict__ Wr, const float *__restrict__ br, int Cin, int C, size_t nframes,
+             __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ R0) {
+    extern __shared__ float sm[];
+    const int K3 = 3 * Cin;
+    float *sA = sm;                                   // [3*17*17]
+    float *sx = sA + 3 * V17 * V17;                   // [FR*17*Cin]
+    float *sxa = sx + kFrontFrames * V17 * Cin;       // [FR*17*3Cin]
+    for (int k = threadIdx.x; k < 3 * V17 * V17; k += blockDim.x) sA[k] = A[k];
+    const size_t f0 = (size_t)blockIdx.x * kFrontFrames;
+    const int nf = (int)(nframes - f0 < (size_t)kFrontFrames ? nframes - f0 : (size_t)kFrontFrames);
+    for (int e = threadIdx.x; e < nf * V17 * Cin; e += blockDim.x) {
+        const int vc = e % (V17 * Cin);
+        sx[e] = skel[f0 * V17 * Cin + e] * in_scale[vc] + in_shift[vc];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nf * V17 * K3; e += blockDim.x) {
+        const int k = e % K3, w = (e / K3) % V17, f = e / (K3 * V17);
+        const int p = k / Cin, c = k % Cin;
+        const float *ar = sA + (p * V17 + w) * V17;
+        const float *xf = sx + f * V17 * Cin + c;
+        float acc = 0.f;
+#pragma unroll
+        for (int v = 0; v < V17; ++v) acc += ar[v] * xf[v * Cin];
+        sxa[e] = acc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nf * V17 * C; e += blockDim.x) {
+        const int co = e % C, row = e / C;
+        const float *xa = sxa + row * K3;
+        float y = bg[co];
+        for (int k = 0; k < K3; ++k) y += xa[k] * Wg[k * C + co];
+        const float *x = sx + row * Cin;
+        float r = br[co];
+        for (int c = 0; c < Cin; ++c) r += x[c] * Wr[c * C + co];
+        const size_t o = (f0 * V17 + row) * C + co;
+        Y[o] = __float2bfloat16_rn(fmaxf(y, 0.f));
+        R0[o] = __float2bfloat16_rn(r);
+    }
+}
+
+int upload_bf16(Ctx *ctx, const std::vector<__nv_bfloat16> &h, __nv_bfloat16 **d) {
+    GS_CUDA(cudaMalloc((void **)d, h.size() * 2));
+    ctx->ws_bytes += h.size() * 2;
+    GS_CUDA(cudaMemcpy(*d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     return GS_OK;
 }
 
-void bf16_path_destroy(Ctx *ctx) { (void)ctx; }
+int build_maps(Ctx *ctx, int T) {
+    Bf16Path *bp = ctx->bf16;
+    if (bp->maps_T == T) return GS_OK;
+    const int rows = T * V17, batch = ctx->max_B;
+    const int R = ctx->cfg.num_branches;
+    bp->maps.assign(ctx->blocks.size(), BlockMaps{});
+    int rc;
+    for (size_t i = 0; i < ctx->blocks.size(); ++i) {
+        const BlockParams &b = ctx->blocks[i];
+        BlockMaps &m = bp->maps[i];
+        const int C = b.c, cin = b.cin, cr = b.cr;
+        if ((rc = tc::make_act_map(&m.y_out, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
+        if ((rc = tc::make_act_map(&m.y_in, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
+        if ((rc = tc::make_act_map(&m.h_out, ctx->bufH, C, rows, batch, 64, tc::kTileM))) return rc;
+        if ((rc = tc::make_act_map(&m.h_in, ctx->bufH, C, rows, batch, cr, tc::kTileM))) return rc;
+        for (int k = 0; k < 2; ++k)
+            if ((rc = tc::make_act_map(&m.u_out[k], ctx->bufU[k], C, rows, batch, 64, tc::kTileM))) return rc;
+        if ((rc = tc::make_weight_map(&m.w1, bp->W1T[i], C, C, 64, C))) return rc;
+        if ((rc = tc::make_weight_map(&m.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
+        if (i > 0) {
+            if ((rc = tc::make_act_map(&m.xa_in, ctx->bufXA, 3 * cin, rows, batch, 64, tc::kTileM))) return rc;
+            if ((rc = tc::make_weight_map(&m.wg, bp->WgT[i], 3 * cin, C, 64, C))) return rc;
+            if (b.has_res) {
+                if ((rc = tc::make_act_map(&m.xg_in, ctx->bufX, cin, rows, batch, cr, tc::kTileM))) return rc;
+                if ((rc = tc::make_weight_map(&m.wr, bp->WrT[i], cin, C, cr, C))) return rc;
+            }
+        }
+    }
+    bp->maps_T = T;
+    return GS_OK;
+}
 
-int segment_bf16_forward(Ctx *, const float *, float *, uint8_t *, int, int, int, float *, cudaStream_t) {
-    set_error("bf16 path not built yet");
-    return GS_ERR_UNSUPPORTED;
+void base_program(tc::Program &p, int B, int T, int N, int kc, int relu) {
+    memset(&p, 0, sizeof(p));
+    p.kc = kc;
+    p.N = N;
+    p.rows_per_clip = T * V17;
+    p.mtiles = cdiv(p.rows_per_clip, tc::kTileM);
+    p.ntiles = B * p.mtiles;
+    p.relu = relu;
+    p.a_bytes = tc::kTileM * kc * 2;
+}
+
+// Out = relu(In[rows,K] . W^T + bias): K in 64-wide chunks
+int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, const CUtensorMap &out,
+               const float *bias, int B, int T, int K, int N, cudaStream_t st) {
+    tc::Launch L{};
+    base_program(L.prog, B, T, N, 64, 1);
+    L.prog.nchunks = K / 64;
+    L.prog.b_bytes[0] = N * 64 * 2;
+    for (int k = 0; k < L.prog.nchunks; ++k) {
+        tc::Chunk &c = L.prog.ch[k];
+        c.a_k = c.b_k = 64 * k;
+        c.n_size = N;
+        c.accum = k > 0;
+    }
+    L.mapA0 = L.mapA1 = in;
+    L.mapB0 = L.mapB1 = w;
+    L.mapOut = out;
+    L.bias = bias;
+    L.maxBrows = N;
+    L.stages = tc::pick_stages(64, N, N);
+    const double rows = (double)B * T * V17;
+    L.flops = 2.0 * rows * K * N;
+    L.bytes = 2.0 * rows * (K + N);
+    return tc::launch(ctx, kid, L, st);
+}
+
+}  // namespace
+
+int bf16_path_create(Ctx *ctx) {
+    const gs_config &c = ctx->cfg;
+    const int R = c.num_branches;
+    if (ctx->blocks.empty() || !ctx->blocks[0].has_res) {
+        set_error("bf16 path expects block 0 to change width (residual projection)");
+        return GS_ERR_UNSUPPORTED;
+    }
+    for (size_t i = 0; i < ctx->blocks.size(); ++i) {
+        const BlockParams &b = ctx->blocks[i];
+        const bool ok = (b.c % 64 == 0) && b.c <= 256 && (b.cr == 16 || b.cr == 32 || b.cr == 64) &&
+                        (i == 0 || (b.cin % 64 == 0 && b.cin % b.cr == 0));
+        if (!ok) {
+            set_error("bf16 tensor-core path needs widths in {64,128,256} and C/R in {16,32,64} "
+                      "(block %zu: cin=%d c=%d c/R=%d); use precision fp32 for this config", i, b.cin, b.c, b.cr);
+            return GS_ERR_UNSUPPORTED;
+        }
+        if ((b.has_res ? b.cin / b.cr : 0) + 3 * R > tc::kMaxChunks) {
+            set_error("chunk program too long for block %zu", i);
+            return GS_ERR_UNSUPPORTED;
+        }
+    }
+    if (!tc::get_encode_fn()) {
+        set_error("cuTensorMapEncodeTiled entry point not found");
+        return GS_ERR_CUDA;
+    }
+    Bf16Path *bp = new Bf16Path();
+    ctx->bf16 = bp;
+    const size_t nb = ctx->blocks.size();
+    bp->WgT.assign(nb, nullptr);
+    bp->W1T.assign(nb, nullptr);
+    bp->W2p.assign(nb, nullptr);
+    bp->WrT.assign(nb, nullptr);
+    bp->bias_t.assign(nb, nullptr);
+    const float *hb = ctx->h_blob.data();
+    auto host = [&](const float *dev_ptr) { return hb + (dev_ptr - ctx->d_blob); };
+    int rc;
+    for (size_t i = 0; i < nb; ++i) {
+        const BlockParams &b = ctx->blocks[i];
+        const int C = b.c, cin = b.cin, cr = b.cr;
+        std::vector<__nv_bfloat16> h;
+        if (i > 0) {   // WgT [C][3cin]
+            const float *W = host(b.Wg);
+            h.assign((size_t)C * 3 * cin, __nv_bfloat16());
+            for (int k = 0; k < 3 * cin; ++k)
+                for (int n = 0; n < C; ++n) h[(size_t)n * 3 * cin + k] = __float2bfloat16_rn(W[(size_t)k * C + n]);
+            if ((rc = upload_bf16(ctx, h, &bp->WgT[i]))) return rc;
+        }
+        {   // W1T [C][C]
+            const float *W = host(b.W1);
+            h.assign((size_t)C * C, __nv_bfloat16());
+            for (int k = 0; k < C; ++k)
+                for (int n = 0; n < C; ++n) h[(size_t)n * C + k] = __float2bfloat16_rn(W[(size_t)k * C + n]);
+            if ((rc = upload_bf16(ctx, h, &bp->W1T[i]))) return rc;
+        }
+        {   // W2p [(r*3+j)*cr + co][ci]
+            const float *W = host(b.W2);
+            h.assign((size_t)R * 3 * cr * cr, __nv_bfloat16());
+            for (int rj = 0; rj < R * 3; ++rj)
+                for (int ci = 0; ci < cr; ++ci)
+                    for (int co = 0; co < cr; ++co)
+                        h[((size_t)rj * cr + co) * cr + ci] =
+                            __float2bfloat16_rn(W[((size_t)rj * cr + ci) * cr + co]);
+            if ((rc = upload_bf16(ctx, h, &bp->W2p[i]))) return rc;
+        }
+        std::vector<float> bias(host(b.b2), host(b.b2) + C);
+        if (i > 0 && b.has_res) {   // WrT [C][cin]; its bias joins b2
+            const float *W = host(b.Wr);
+            h.assign((size_t)C * cin, __nv_bfloat16());
+            for (int k = 0; k < cin; ++k)
+                for (int n = 0; n < C; ++n) h[(size_t)n * cin + k] = __float2bfloat16_rn(W[(size_t)k * C + n]);
+            if ((rc = upload_bf16(ctx, h, &bp->WrT[i]))) return rc;
+            const float *brh = host(b.br);
+            for (int n = 0; n < C; ++n) bias[n] += brh[n];
+        }
+        GS_CUDA(cudaMalloc((void **)&bp->bias_t[i], C * sizeof(float)));
+        GS_CUDA(cudaMemcpy(bp->bias_t[i], bias.data(), C * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return GS_OK;
+}
+
+void bf16_path_destroy(Ctx *ctx) {
+    Bf16Path *bp = ctx->bf16;
+    if (!bp) return;
+    for (auto *v : {&bp->WgT, &bp->W1T, &bp->W2p, &bp->WrT})
+        for (__nv_bfloat16 *p : *v)
+            if (p) cudaFree(p);
+    for (float *p : bp->bias_t)
+        if (p) cudaFree(p);
+    delete bp;
+    ctx->bf16 = nullptr;
+}
+
+int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,
+                         int upto_block, float *feat_out, cudaStream_t st) {
+    typedef __nv_bfloat16 bf;
+    Bf16Path *bp = ctx->bf16;
+    int rc;
+    if ((rc = build_maps(ctx, T))) return rc;
+    const size_t nframes = (size_t)B * T;
+    const double rows = (double)nframes * V17;
+    const int nb = ctx->cfg.num_blocks, R = ctx->cfg.num_branches;
+    const int last = upto_block >= 0 ? upto_block : nb - 1;
+    bf *X = (bf *)ctx->bufX, *XA = (bf *)ctx->bufXA, *Y = (bf *)ctx->bufY, *R0 = (bf *)ctx->bufR;
+    const bf *Uprev = nullptr;
+    for (int i = 0; i <= last; ++i) {
+        const BlockParams &b = ctx->blocks[i];
+        const BlockMaps &m = bp->maps[i];
+        const int C = b.c, cin = b.cin, cr = b.cr;
+        bf *U = (bf *)ctx->bufU[i & 1];
+        if (i == 0) {
+            const size_t smem = (3 * V17 * V17 + kFrontFrames * V17 * cin * 4) * sizeof(float);
+            {
+                LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
+                               rows * (cin * 4 + 4.0 * C));
+                front_kernel<<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
+                    skel, ctx->in_scale, ctx->in_shift, b.A, b.Wg, b.bg, b.Wr, b.br, cin, C, nframes, Y, R0);
+            }
+            GS_KERNEL_CHECK();
+        } else {
+            const size_t items = nframes * cin;
+            size_t g = (items + 255) / 256;
+            if (g > (size_t)ctx->sm_count * 32) g = (size_t)ctx->sm_count * 32;
+            {
+                LaunchScope ls(ctx, K_B_AGG, st, 2.0 * rows * V17 * 3 * cin, 2.0 * rows * cin * 5);
+                aggregate_kernel<bf, bf, 3><<<(int)g, 256, 0, st>>>(Uprev, ctx->gT, ctx->gV, nullptr, nullptr, b.A, T,
+                                                                   cin, nframes, X, XA);
+            }
+            GS_KERNEL_CHECK();
+            if ((rc = dense_gemm(ctx, K_B_GEMM_GCN, m.xa_in, m.wg, m.y_out, b.bg, B, T, 3 * cin, C, st))) return rc;
+        }
+        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out, b.b1, B, T, C, C, st))) return rc;
+        {   // dilated taps (+ residual projection) + residual + ReLU
+            tc::Launch L{};
+            base_program(L.prog, B, T, C, cr, 1);
+            const bool proj = (i > 0 && b.has_res);
+            int n = 0;
+            if (proj) {
+                for (int k = 0; k < cin / cr; ++k) {
+                    tc::Chunk &c = L.prog.ch[n++];
+                    c.a_map = 1;
+                    c.b_map = 1;
+                    c.a_k = c.b_k = k * cr;
+                    c.n_size = C;
+                    c.accum = k > 0;
+                }
+            }
+            for (int r = 0; r < R; ++r)
+                for (int j = 0; j < 3; ++j) {
+                    tc::Chunk &c = L.prog.ch[n++];
+                    c.a_k = r * cr;
+                    c.a_shift = (j - 1) * ctx->cfg.dilations[r] * V17;
+                    c.b_row = (r * 3 + j) * cr;
+                    c.n_off = r * cr;
+                    c.n_size = cr;
+                    c.accum = proj || j > 0;
+                }
+            L.prog.nchunks = n;
+            L.prog.b_bytes[0] = cr * cr * 2;
+            L.prog.b_bytes[1] = C * cr * 2;
+            L.prog.has_residual = proj ? 0 : 1;
+            L.residual = proj ? nullptr : (i == 0 ? R0 : X);
+            L.mapA0 = m.h_in;
+            L.mapB0 = m.w2;
+            L.mapA1 = proj ? m.xg_in : m.h_in;
+            L.mapB1 = proj ? m.wr : m.w2;
+            L.mapOut = m.u_out[i & 1];
+            L.bias = bp->bias_t[i];
+            L.maxBrows = proj ? C : cr;
+            L.stages = tc::pick_stages(cr, L.maxBrows, C);
+            L.flops = 2.0 * rows * (3.0 * cr * C + (proj ? (double)cin * C : 0.0));
+            L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
+            if ((rc = tc::launch(ctx, K_B_TCONV, L, st))) return rc;
+        }
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st))) return rc;
+        Uprev = U;
+    }
+    const int C = ctx->blocks[last].c;
+    if (feat_out) return launch_features<bf>(ctx, Uprev, B, T, C, feat_out, st);
+    return launch_head<bf>(ctx, Uprev, B, T, C, logits, labels, st);
 }
 
 }  // namespace gs

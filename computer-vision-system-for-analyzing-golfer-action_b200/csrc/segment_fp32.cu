@@ -10,56 +10,6 @@ namespace gs {
 
 namespace {
 
-constexpr int V17 = 17;
-
-// ---- gate-on-load + adjacency contraction --------------------------------------
-// Xg[row, c]          = gated input (block 0: skel*scale+shift; else U*gT*gV)
-// XA[row(w), p*Cin+c] = sum_v A[p,w,v] * Xg[frame, v, c]
-// one work item = (frame, channel); A staged in shared memory.
-template <typename TIN, typename TOUT, int P>
-__global__ void __launch_bounds__(256)
-aggregate_kernel(const TIN *__restrict__ Uin, const float *__restrict__ gT, const float *__restrict__ gV,
-                 const float *__restrict__ in_scale, const float *__restrict__ in_shift,
-                 const float *__restrict__ A, int T, int Cin, size_t nframes, TOUT *__restrict__ Xg,
-                 TOUT *__restrict__ XA) {
-    __shared__ float sA[P * V17 * V17];
-    for (int k = threadIdx.x; k < P * V17 * V17; k += blockDim.x) sA[k] = A[k];
-    __syncthreads();
-    const size_t items = nframes * Cin;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-         it += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(it % Cin);
-        const size_t f = it / Cin;           // frame index = b*T + t
-        const size_t b = f / T;
-        float x[V17];
-        const TIN *src = Uin + (f * V17) * Cin + c;
-        if (in_scale) {
-#pragma unroll
-            for (int v = 0; v < V17; ++v)
-                x[v] = ld_act(src + (size_t)v * Cin) * in_scale[v * Cin + c] + in_shift[v * Cin + c];
-        } else {
-            const float gt = gT[f * Cin + c];
-            const float *gv = gV + (b * V17) * Cin + c;
-#pragma unroll
-            for (int v = 0; v < V17; ++v) x[v] = ld_act(src + (size_t)v * Cin) * gt * gv[(size_t)v * Cin];
-        }
-        TOUT *xg = Xg + (f * V17) * Cin + c;
-#pragma unroll
-        for (int v = 0; v < V17; ++v) st_act(xg + (size_t)v * Cin, x[v]);
-        TOUT *xa = XA + (f * V17) * (size_t)(P * Cin) + c;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            for (int w = 0; w < V17; ++w) {
-                const float *ar = sA + (p * V17 + w) * V17;
-                float acc = 0.f;
-#pragma unroll
-                for (int v = 0; v < V17; ++v) acc += ar[v] * x[v];
-                st_act(xa + (size_t)w * (P * Cin) + p * Cin, acc);
-            }
-        }
-    }
-}
-
 // ---- SIMT row GEMM: Out[M,N] = act(In[M,K] @ W[K,N] + bias) ------------------------
 // 64x64 tile, BK=16, 256 threads, 4x4 outputs per thread; any M,N,K (guarded).
 template <bool RELU>

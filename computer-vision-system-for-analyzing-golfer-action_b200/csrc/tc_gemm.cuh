@@ -1,0 +1,495 @@
+// tcgen05 / TMEM / TMA "tap GEMM" for sm_100a — the dense contractions of the bf16 path.
+//
+//   Out[b, r, n] = act( sum_chunks  A_chunk[b, r + shift, k..k+KC) . B_chunk[n, k..k+KC)  + bias[n]
+//                       (+ residual[b, r, n]) )            bf16 in, fp32 accumulate in TMEM, bf16 out
+//
+// A "chunk" is one TMA box of the A operand (128 rows x KC bf16, rows optionally shifted
+// in time: OOB rows of the [C, T*V, B] tensor map are zero-filled by TMA, which is exactly
+// the zero padding of the dilated temporal convolution) times one TMA box of weights,
+// accumulated into a column range [n_off, n_off+n_size) of the CTA's TMEM accumulator.
+// One chunk program therefore expresses
+//   * the graph-conv channel mix        (K = 3*Cin in 64-wide chunks, N = C),
+//   * the branch 1x1 reduce             (K = C, N = C),
+//   * the multi-branch dilated conv     (per branch r, 3 shifted taps, K = N = C/R, n_off = r*C/R)
+//     fused with the residual projection (extra chunks, K = Cin, N = C) and the final add+ReLU.
+// Stages replaced: /root/reference/README.md:27-30.
+//
+// Warp roles (256 threads, persistent over (clip, row-tile) tiles, 1 CTA per SM):
+//   warp 0  TMA producer      warp 1  tcgen05.mma issuer (one elected lane)
+//   warp 2  TMEM allocator    warps 4-7  epilogue: tcgen05.ld -> bias/residual/ReLU -> bf16 ->
+//                                        swizzled smem -> TMA store
+// Pipelines: smem ring (full/empty mbarriers) and a double-buffered TMEM accumulator
+// (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gs {
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kMaxChunks = 32;
+constexpr int kThreads = 256;
+
+struct Chunk {
+    int a_map;    // 0 / 1: which A tensor map
+    int b_map;    // 0 / 1: which B tensor map
+    int a_k;      // channel coordinate in the A map
+    int a_shift;  // row shift (frames * V) applied to the tile's first row
+    int b_k;      // k coordinate in the B map
+    int b_row;    // row (n) coordinate in the B map
+    int n_off;    // accumulator column offset
+    int n_size;   // N of this MMA (multiple of 16, 16..256)
+    int accum;    // 0: first chunk touching these columns (overwrite), 1: accumulate
+};
+
+struct Program {
+    int nchunks;
+    int kc;             // K elements per chunk: 16, 32 or 64  (swizzle = 2*kc bytes)
+    int N;              // accumulator columns used (multiple of 64, <= 256)
+    int mtiles;         // row tiles per clip
+    int ntiles;         // total tiles = B * mtiles
+    int rows_per_clip;  // T * V
+    int relu;
+    int has_residual;   // add residual[b, r, n] (bf16, row stride N) before the activation
+    int a_bytes;        // bytes of one A box
+    int b_bytes[2];     // bytes of one B box per B map
+    Chunk ch[kMaxChunks];
+};
+
+// ------------------------------------------------------------------ PTX wrappers ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a pipeline bug traps (a reported CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    printf("tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, bf16 x bf16 -> fp32, cta_group::1
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): rows of
+// `row_bytes` (= swizzle span: 32 / 64 / 128 B), 8-row groups SBO = 8*row_bytes apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address  [0,14)
+    d |= (uint64_t)1 << 16;                               // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)((8u * row_bytes) >> 4) << 32;         // SBO [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version = 1 (sm_100)
+    d |= layout << 61;                                    // swizzle mode [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: A=B=bf16 (1), D=fp32 (1), both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct SmemPlan {
+    uint32_t stage_bytes, a_bytes, out_off, bar_off, total;
+    int stages;
+};
+
+__host__ __device__ inline SmemPlan smem_plan(int kc, int maxBrows, int N, int stages) {
+    SmemPlan p;
+    p.a_bytes = (uint32_t)kTileM * kc * 2;
+    uint32_t bb = (uint32_t)maxBrows * kc * 2;
+    bb = (bb + 1023u) & ~1023u;
+    p.stage_bytes = ((p.a_bytes + 1023u) & ~1023u) + bb;
+    p.stages = stages;
+    p.out_off = p.stage_bytes * stages;
+    p.bar_off = p.out_off + (uint32_t)kTileM * N * 2;
+    p.total = p.bar_off + 256 + 1024;   // barriers + slack for the manual 1024 B alignment
+    return p;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ Program prog,
+               const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual, int maxBrows) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const SmemPlan plan = smem_plan(prog.kc, maxBrows, prog.N, STAGES);
+    const uint32_t a_span = (plan.a_bytes + 1023u) & ~1023u;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tfull = empty + STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int N = prog.N;
+    const uint32_t tmem_cols = (2 * N <= 128) ? 128u : (2 * N <= 256 ? 256u : 512u);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB0);
+        tma_prefetch_desc(&mapB1);
+        tma_prefetch_desc(&mapOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+                const int b = tile / prog.mtiles;
+                const int row0 = (tile % prog.mtiles) * kTileM;
+                for (int c = 0; c < prog.nchunks; ++c) {
+                    const Chunk &ch = prog.ch[c];
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char *sa = smem + (size_t)stage * plan.stage_bytes;
+                    unsigned char *sb = sa + a_span;
+                    mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes + (uint32_t)prog.b_bytes[ch.b_map]);
+                    tma_load_3d(sa, ch.a_map ? &mapA1 : &mapA0, &full[stage], ch.a_k, row0 + ch.a_shift, b);
+                    tma_load_2d(sb, ch.b_map ? &mapB1 : &mapB0, &full[stage], ch.b_k, ch.b_row);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t row_bytes = (uint32_t)prog.kc * 2;
+            const int ksteps = prog.kc / 16;
+            for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * N);
+                for (int c = 0; c < prog.nchunks; ++c) {
+                    const Chunk &ch = prog.ch[c];
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * plan.stage_bytes);
+                    const uint64_t da = make_kmajor_desc(sa, row_bytes);
+                    const uint64_t db = make_kmajor_desc(sa + a_span, row_bytes);
+                    const uint32_t idesc = make_idesc_bf16((uint32_t)ch.n_size);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // +32 bytes of K per step: descriptor start address is in 16 B units
+                        umma_bf16(tacc + (uint32_t)ch.n_off, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (uint32_t)(ch.accum | (k > 0)));
+                    }
+                    umma_commit(&empty[stage]);          // frees this smem stage once the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows =====
+        const int ew = warp - 4;
+        const int r = ew * 32 + lane;                  // row inside the tile
+        const bool leader = (threadIdx.x == 128);
+        unsigned char *sout = smem + plan.out_off;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+            const int b = tile / prog.mtiles;
+            const int row0 = (tile % prog.mtiles) * kTileM;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            // staging buffer must no longer be read by the previous tile's TMA store
+            if (leader) tma_store_wait_read0();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool row_ok = (row0 + r) < prog.rows_per_clip;
+            const __nv_bfloat16 *res_row =
+                residual + ((size_t)b * prog.rows_per_clip + (size_t)(row0 + r)) * (size_t)N;
+            for (int q = 0; q < N / 64; ++q) {
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N + q * 64);
+                tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                unsigned char *box = sout + (size_t)q * (kTileM * 128);
+#pragma unroll
+                for (int cchunk = 0; cchunk < 8; ++cchunk) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        f[e] = __uint_as_float(v[cchunk * 8 + e]) + __ldg(bias + q * 64 + cchunk * 8 + e);
+                    if (prog.has_residual && row_ok) {
+                        const uint4 rr = *reinterpret_cast<const uint4 *>(res_row + q * 64 + cchunk * 8);
+                        const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 t = __bfloat1622float2(rp[e]);
+                            f[2 * e] += t.x;
+                            f[2 * e + 1] += t.y;
+                        }
+                    }
+                    if (prog.relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+                    uint4 packed;
+                    __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&packed);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                    // 128B-swizzled box row: 16 B chunk index XOR (row & 7) — matches the TMA map
+                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cchunk ^ (r & 7)) << 4)) = packed;
+                }
+            }
+            // TMEM reads of this accumulator are done (wait::ld above): hand it back to the MMA warp
+            tc_fence_before();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+                mbar_arrive(&tempty[acc]);
+                for (int q = 0; q < N / 64; ++q)
+                    tma_store_3d(&mapOut, sout + (size_t)q * (kTileM * 128), q * 64, row0, b);
+                tma_store_commit();
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (leader) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 [batch, rows, width] activation (row-major, width contiguous) -> 3-D map, box (box_w, box_rows, 1)
+inline int make_act_map(CUtensorMap *m, const void *base, int width, int rows, int batch, int box_w,
+                        int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return GS_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)width * 2 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_w * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(act %dx%dx%d box %dx%d) failed: %d", width, rows, batch, box_w, box_rows,
+                  (int)r);
+        return GS_ERR_CUDA;
+    }
+    return GS_OK;
+}
+
+// bf16 [nrows, kwidth] weight matrix (K contiguous) -> 2-D map, box (box_k, box_rows)
+inline int make_weight_map(CUtensorMap *m, const void *base, int kwidth, int nrows, int box_k, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return GS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kwidth, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)kwidth * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_k * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weight %dx%d box %dx%d) failed: %d", kwidth, nrows, box_k, box_rows,
+                  (int)r);
+        return GS_ERR_CUDA;
+    }
+    return GS_OK;
+}
+
+struct Launch {
+    CUtensorMap mapA0, mapA1, mapB0, mapB1, mapOut;
+    Program prog;
+    const float *bias = nullptr;
+    const __nv_bfloat16 *residual = nullptr;
+    int maxBrows = 0;
+    int stages = 4;
+    double flops = 0, bytes = 0;   // algorithmic, for the profiler
+};
+
+inline int pick_stages(int kc, int maxBrows, int N) {
+    const int cand[4] = {6, 4, 3, 2};
+    for (int s : cand)
+        if (smem_plan(kc, maxBrows, N, s).total <= 227u * 1024u) return s;
+    return 0;
+}
+
+inline int launch(Ctx *ctx, int kid, const Launch &L, cudaStream_t st) {
+    const SmemPlan plan = smem_plan(L.prog.kc, L.maxBrows, L.prog.N, L.stages);
+    int grid = L.prog.ntiles < ctx->sm_count ? L.prog.ntiles : ctx->sm_count;
+    if (grid < 1) return GS_OK;
+#define GS_TC_LAUNCH(S)                                                                                        \
+    do {                                                                                                       \
+        GS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                     (int)plan.total));                                                        \
+        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);                                                        \
+        tc_gemm_kernel<S><<<grid, kThreads, plan.total, st>>>(L.mapA0, L.mapA1, L.mapB0, L.mapB1, L.mapOut,    \
+                                                              L.prog, L.bias, L.residual, L.maxBrows);         \
+    } while (0)
+    switch (L.stages) {
+        case 2: GS_TC_LAUNCH(2); break;
+        case 3: GS_TC_LAUNCH(3); break;
+        case 4: GS_TC_LAUNCH(4); break;
+        case 6: GS_TC_LAUNCH(6); break;
+        default:
+            set_error("tc_gemm: unsupported stage count %d", L.stages);
+            return GS_ERR_UNSUPPORTED;
+    }
+#undef GS_TC_LAUNCH
+    GS_KERNEL_CHECK();
+    return GS_OK;
+}
+
+}  // namespace tc
+}  // namespace gs
