@@ -38,7 +38,7 @@ PAIRS = 4096         # BASELINE.json configs[2]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("GOLFER_PRECISION", "bf16"),
@@ -248,12 +248,14 @@ def main():
             dist.all_gather_into_tensor(gathered, logits)
         return logits
 
-    for _ in range(W):
-        seg_step()
-    barrier()
+    # nvidia-smi needs ~0.2 s before its first sample: start it before the warm-up and keep
+    # only samples taken under load (clocks.sm above half of max) for the median
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        seg_step()
+    barrier()
     seg.ctx.profile_reset()
     seg.ctx.profile(True)
     l0 = seg.ctx.launch_count()
@@ -265,7 +267,6 @@ def main():
     barrier()
     seg.ctx.profile(False)
     launches = seg.ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     seg_ms = max_over_ranks(e0.elapsed_time(e1))
     prof = seg.ctx.profile_read()
     value = world * B * K / (seg_ms * 1e-3)
@@ -364,6 +365,8 @@ def main():
                                  "throughput (~1.5-3 M pairs/s per GPU), not HBM (SURVEY.md 7 item 4)",
                          "instr_bound_pairs_per_s_per_gpu": 1.5e6},
         }
+
+    clocks = sampler.stop() if rank == 0 else None   # covers every timed region above
 
     # ---- CPU oracle timed beside it (rank 0, N=1 only; bounded sample) ---------------
     cpu_baseline = None

@@ -1,0 +1,86 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into profiles/ (tracked).
+
+    python tools/ncu_summary.py <tag> [--launches gpurun_out/launches.csv] [--rep gpurun_out/prof.ncu-rep]
+"""
+import argparse
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed.sum", "smsp__inst_executed.sum",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "l1tex__t_bytes.sum", "lts__t_bytes.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def short(name):
+    return name.split("(")[0].replace("void ", "").replace("gs::", "").replace("(anonymous namespace)::", "")
+
+
+def launches_table(path):
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
+        d = agg.setdefault(short(r[ki]), [0, 0.0])
+        d[0] += 1
+        d[1] += v
+    tot = sum(v[1] for v in agg.values())
+    out = ["| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / tot:.3f} |")
+    out.append(f"\n{len(rows) - 1} launches captured, {tot / 1e3:.2f} ms of kernel time (ncu-serialised, cold cache: compare shares).")
+    return "\n".join(out)
+
+
+def rep_table(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    cols = [(m, hdr.index(m)) for m in METRICS if m in hdr]
+    ki = hdr.index("Kernel Name")
+    out = ["| # | kernel | " + " | ".join(f"{m} [{units[i]}]" for m, i in cols) + " |",
+           "|---|---|" + "---:|" * len(cols)]
+    for n, r in enumerate(rows[2:]):
+        out.append(f"| {n} | `{short(r[ki])}` | " + " | ".join(r[i] for _, i in cols) + " |")
+    return "\n".join(out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("tag")
+    ap.add_argument("--launches")
+    ap.add_argument("--rep")
+    ap.add_argument("--cmd", default="")
+    ap.add_argument("--note", default="")
+    a = ap.parse_args()
+    out = [f"# ncu summary — {a.tag}", ""]
+    if a.cmd:
+        out += [f"Command profiled: `{a.cmd}`", ""]
+    if a.note:
+        out += [a.note, ""]
+    if a.launches:
+        out += ["## Launch list (`--metrics gpu__time_duration.sum --clock-control none`)", "",
+                launches_table(a.launches), ""]
+    if a.rep:
+        out += ["## Full capture (`--set full --clock-control none --import-source on`)", "", rep_table(a.rep), ""]
+    path = os.path.join(ROOT, "profiles", f"{a.tag}.md")
+    open(path, "w").write("\n".join(out))
+    print(path)
+
+
+if __name__ == "__main__":
+    main()
