@@ -1,0 +1,446 @@
+// Fused spatial graph convolution for sm_100a (blocks with Cin >= 64):
+//
+//   Xg = U_prev * gT * gV                         (deferred attention gates, applied on load)
+//   XA[w, p*Cin + c] = sum_v A_p[w,v] * Xg[v, c]  (adjacency contraction, per frame)
+//   Y  = relu(XA . Wg + bg)                       (1x1 channel mix, K = 3*Cin)
+//
+// in ONE kernel: neither XA (3x the input) nor an un-gated copy of the input ever reaches HBM.
+// Stage replaced: /root/reference/README.md:27-28 (Spatial Module - Graph Convolution).
+//
+// A tile is 7 whole frames (119 rows, padded to the 128-row UMMA M).  Both contractions run on
+// tcgen05 tensor cores:
+//   MMA1 (TS form)  D1[128 x 64]  = Abig_p[128 x 128] . Xg[128 rows x 64 ch]
+//        Abig_p = I_7 (x) A_p, the block-diagonal adjacency, lives in TENSOR MEMORY as the
+//        A operand (bf16, 64 columns per partition); Xg is the TMA-loaded tile itself, used
+//        in place as an MN-major B operand (channels contiguous).
+//   convert         D1 (fp32, TMEM) -> bf16 -> 128B-swizzled K-major smem chunk
+//   MMA2 (SS form)  acc[128 x C] += XAchunk[128 x 64] . WgT[C x 64]^T     (TMA weight ring)
+// TMEM map (512 columns): [0,C) acc | [256,320) D1 | [320,512) Abig_0..2.
+//
+// Warp roles (384 threads, persistent, 1 CTA/SM):
+//   w0 X-tile TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
+//   w4-7  TMEM warps: build Abig (once), convert D1 -> XA chunks, epilogue (bias, ReLU, TMA store)
+//   w8-11 gate warps: multiply the landed tile by gT*gV in place, TMA-store it as Xg
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace gs {
+namespace gcn {
+
+using namespace tc;
+
+constexpr int kThreadsGcn = 384;
+constexpr int kFramesPerTile = 7;
+constexpr int kRowsPerTile = kFramesPerTile * 17;   // 119
+constexpr int kColD1 = 256;
+constexpr int kColAbig = 320;
+
+struct Params {
+    int Cin, C, T, B;
+    int mtiles, ntiles, rows_per_clip;
+    int wstages;
+    const float *gT;      // [B,T,Cin]   (nullptr: no gating)
+    const float *gV;      // [B,17,Cin]
+    const float *A;       // [3,17,17] fp32
+    const float *bias;    // [C]
+    __nv_bfloat16 *dbg_xa;   // optional [ntiles*128, 3*Cin] dump of the converted XA chunks
+};
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major (channels contiguous) SW128 operand: rows of the K dimension are 128 B apart, 8-row groups
+// 1024 B apart (SBO); LBO = distance between 64-element MN blocks (unused here: N = 64 = one block).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(16384 >> 4) << 16;    // LBO
+    d |= (uint64_t)(1024 >> 4) << 32;     // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+// A: bf16 from TMEM (K-major), B: bf16 MN-major from smem, D fp32, M=128, N=64
+__device__ __forceinline__ uint32_t make_idesc_agg() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct Smem {
+    uint32_t x_off, w_off, xa_off, bar_off, total, w_stage_bytes;
+};
+__host__ __device__ inline Smem smem_layout(int Cin, int C, int wstages) {
+    Smem s;
+    s.x_off = 0;
+    s.w_off = (uint32_t)(Cin / 64) * 16384u;
+    s.w_stage_bytes = (uint32_t)C * 128u;
+    s.xa_off = s.w_off + s.w_stage_bytes * wstages;
+    s.bar_off = s.xa_off + 2u * 16384u;
+    s.total = s.bar_off + 512 + 1024;
+    return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int WSTAGES>
+__global__ void __launch_bounds__(kThreadsGcn, 1)
+gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXg,
+                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
+                 const __grid_constant__ Params prm) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const Smem lay = smem_layout(prm.Cin, prm.C, WSTAGES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar_off);
+    uint64_t *x_full = bars + 0, *x_ready = bars + 1, *x_empty = bars + 2;
+    uint64_t *d1_full = bars + 3, *d1_empty = bars + 4;
+    uint64_t *xa_full = bars + 5;    // [2]
+    uint64_t *xa_empty = bars + 7;   // [2]
+    uint64_t *acc_full = bars + 9, *acc_empty = bars + 10;
+    uint64_t *w_full = bars + 11;              // [WSTAGES]
+    uint64_t *w_empty = w_full + WSTAGES;      // [WSTAGES]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_empty + WSTAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cin = prm.Cin, C = prm.C;
+    const int nbc = Cin / 64;       // 64-channel boxes of the input tile
+    const int nq = 3 * nbc;         // XA chunks (= K chunks of the channel mix) per tile
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapXg);
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapY);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(x_full, 1);
+        mbar_init(x_ready, 1);
+        mbar_init(x_empty, 2);          // MMA1 commit + Xg store drained
+        mbar_init(d1_full, 1);
+        mbar_init(d1_empty, 128);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&xa_full[s], 128);
+            mbar_init(&xa_empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 128);
+        for (int s = 0; s < WSTAGES; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- one-time: block-diagonal adjacency Abig_p = I_7 (x) A_p into tensor memory --------
+    if (warp >= 4 && warp < 8) {
+        const int r = (warp - 4) * 32 + lane;          // output row (w of frame f)
+        const int f = r / 17, w = r % 17;
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t regs[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int k0 = half * 64 + 2 * j;   // columns (input rows) k0, k0+1
+                    float a0 = 0.f, a1 = 0.f;
+                    if (r < kRowsPerTile) {
+                        if (k0 / 17 == f && k0 < kRowsPerTile) a0 = prm.A[(p * 17 + w) * 17 + (k0 % 17)];
+                        if ((k0 + 1) / 17 == f && k0 + 1 < kRowsPerTile) a1 = prm.A[(p * 17 + w) * 17 + ((k0 + 1) % 17)];
+                    }
+                    regs[j] = pack_bf16(a0, a1);
+                }
+                tmem_st32(tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(kColAbig + p * 64 + half * 32),
+                          regs);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===== X-tile producer =====
+        if (lane == 0) {
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+                const int b = tile / prm.mtiles;
+                const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+                mbar_wait(x_empty, ph ^ 1);
+                mbar_expect_tx(x_full, (uint32_t)nbc * 16384u);
+                for (int cb = 0; cb < nbc; ++cb)
+                    tma_load_3d(smem + lay.x_off + (size_t)cb * 16384, &mapX, x_full, cb * 64, row0, b);
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 3) {
+        // ===== weight-ring producer: chunk q of every tile is WgT[:, q*64 .. q*64+64) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+                for (int q = 0; q < nq; ++q) {
+                    mbar_wait(&w_empty[stage], ph ^ 1);
+                    mbar_expect_tx(&w_full[stage], lay.w_stage_bytes);
+                    tma_load_2d(smem + lay.w_off + (size_t)stage * lay.w_stage_bytes, &mapW, &w_full[stage], q * 64, 0);
+                    if (++stage == WSTAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc_agg();
+            const uint32_t idesc2 = make_idesc_bf16((uint32_t)C);
+            const uint32_t t_acc = tmem_base, t_d1 = tmem_base + kColD1, t_ab = tmem_base + kColAbig;
+            uint32_t tile_ph = 0;       // x_ready / acc_empty phase
+            uint32_t d1_cnt = 0;        // running count of D1 uses
+            uint32_t xa_cnt = 0;        // running count of XA chunks consumed
+            int wstage = 0;
+            uint32_t wph = 0;
+            auto issue_mma2 = [&](int j) {
+                const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
+                if (j == 0) mbar_wait(acc_empty, tile_ph ^ 1);   // previous tile's epilogue has drained acc
+                mbar_wait(&xa_full[slot], ph);
+                mbar_wait(&w_full[wstage], wph);
+                tc_fence_after();
+                const uint64_t da = make_kmajor_desc(smem_u32(smem + lay.xa_off + slot * 16384u), 128);
+                const uint64_t db = make_kmajor_desc(smem_u32(smem + lay.w_off + (size_t)wstage * lay.w_stage_bytes), 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(t_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (uint32_t)((j > 0) | (k > 0)));
+                umma_commit(&xa_empty[slot]);
+                umma_commit(&w_empty[wstage]);
+                ++xa_cnt;
+                if (++wstage == WSTAGES) { wstage = 0; wph ^= 1; }
+            };
+            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+                mbar_wait(x_ready, tile_ph);
+                tc_fence_after();
+                for (int q = 0; q < nq; ++q) {
+                    const int p = q / nbc, cb = q % nbc;
+                    mbar_wait(d1_empty, (d1_cnt & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)cb * 16384);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        // 16 input rows per step: +8 TMEM columns of Abig, +2048 B (two 8-row groups) of X
+                        umma_bf16_ts(t_d1, t_ab + (uint32_t)(p * 64 + k * 8), make_mnmajor_desc(xb + k * 2048), idesc1,
+                                     (uint32_t)(k > 0));
+                    }
+                    umma_commit(d1_full);
+                    ++d1_cnt;
+                    if (q == nq - 1) umma_commit(x_empty);     // every MMA1 of this tile has read X
+                    if (q > 0) issue_mma2(q - 1);
+                }
+                issue_mma2(nq - 1);
+                umma_commit(acc_full);
+                tile_ph ^= 1;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== TMEM warps: convert D1 -> XA chunks, then the tile epilogue =====
+        const int ew = warp - 4;
+        const int r = ew * 32 + lane;
+        const bool leader = (threadIdx.x == 128);
+        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        uint32_t d1_cnt = 0, xa_cnt = 0, tile_ph = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            const int b = tile / prm.mtiles;
+            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+            for (int q = 0; q < nq; ++q) {
+                uint32_t v[64];
+                mbar_wait(d1_full, d1_cnt & 1);
+                tc_fence_after();
+                tmem_ld32(tmem_base + lane_base + kColD1, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld32(tmem_base + lane_base + kColD1 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(d1_empty);              // D1 may be overwritten by the next MMA1
+                ++d1_cnt;
+                const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
+                mbar_wait(&xa_empty[slot], ph ^ 1);  // MMA2 that last read this slot has retired
+                unsigned char *box = smem + lay.xa_off + slot * 16384u;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    uint4 pk;
+                    pk.x = pack_bf16(__uint_as_float(v[cc * 8 + 0]), __uint_as_float(v[cc * 8 + 1]));
+                    pk.y = pack_bf16(__uint_as_float(v[cc * 8 + 2]), __uint_as_float(v[cc * 8 + 3]));
+                    pk.z = pack_bf16(__uint_as_float(v[cc * 8 + 4]), __uint_as_float(v[cc * 8 + 5]));
+                    pk.w = pack_bf16(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
+                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+                    if (prm.dbg_xa)
+                        *reinterpret_cast<uint4 *>(prm.dbg_xa + ((size_t)tile * 128 + r) * (size_t)(3 * Cin) + q * 64 + cc * 8) = pk;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&xa_full[slot]);
+                ++xa_cnt;
+            }
+            // ---- epilogue: acc -> +bias, ReLU -> bf16 -> staging (the XA slots) -> TMA store ----
+            mbar_wait(acc_full, tile_ph);
+            tc_fence_after();
+            for (int qb = 0; qb < C / 64; ++qb) {
+                uint32_t v[64];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(qb * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(qb * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                if (qb == C / 64 - 1) {
+                    tc_fence_before();
+                    mbar_arrive(acc_empty);          // accumulator fully read
+                }
+                const int sb = qb & 1;
+                if (qb >= 2) {                        // staging slot reuse: its previous store must be drained
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                unsigned char *box = smem + lay.xa_off + sb * 16384u;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        f[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + __ldg(prm.bias + qb * 64 + cc * 8 + e), 0.f);
+                    uint4 pk;
+                    pk.x = pack_bf16(f[0], f[1]);
+                    pk.y = pack_bf16(f[2], f[3]);
+                    pk.z = pack_bf16(f[4], f[5]);
+                    pk.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    tma_store_3d(&mapY, box, qb * 64, row0, b);
+                    tma_store_commit();
+                }
+            }
+            // the staging slots become XA slots again for the next tile
+            if (leader) tma_store_wait_read0();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tile_ph ^= 1;
+        }
+        if (leader) tma_store_wait_all0();
+    } else if (warp >= 8) {
+        // ===== gate warps: Xg = X * gT * gV in place, then TMA-store Xg =====
+        const int gt_id = threadIdx.x - 256;          // 0..127
+        const bool leader = (gt_id == 0);
+        const int cpr = Cin / 8;                      // 16-byte chunks per row
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            const int b = tile / prm.mtiles;
+            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+            mbar_wait(x_full, ph);
+            if (prm.gT) {
+                for (int idx = gt_id; idx < kTileM * cpr; idx += 128) {
+                    const int r = idx / cpr, ch = idx % cpr;
+                    const int grow = row0 + r;
+                    if (grow >= prm.rows_per_clip) continue;     // TMA zero-filled
+                    const int t = grow / 17, v = grow % 17;
+                    const int cb = ch >> 3, cc = ch & 7;
+                    uint4 *sp = reinterpret_cast<uint4 *>(smem + lay.x_off + (size_t)cb * 16384 + (size_t)r * 128 +
+                                                          ((cc ^ (r & 7)) << 4));
+                    uint4 x = *sp;
+                    const float4 *gt = reinterpret_cast<const float4 *>(prm.gT + ((size_t)b * prm.T + t) * Cin + ch * 8);
+                    const float4 *gv = reinterpret_cast<const float4 *>(prm.gV + ((size_t)b * 17 + v) * Cin + ch * 8);
+                    const float4 t0 = __ldg(gt), t1 = __ldg(gt + 1), v0 = __ldg(gv), v1 = __ldg(gv + 1);
+                    const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
+                    const float2 a = __bfloat1622float2(xp[0]), c2 = __bfloat1622float2(xp[1]);
+                    const float2 d = __bfloat1622float2(xp[2]), e = __bfloat1622float2(xp[3]);
+                    uint4 o;
+                    o.x = pack_bf16(a.x * t0.x * v0.x, a.y * t0.y * v0.y);
+                    o.y = pack_bf16(c2.x * t0.z * v0.z, c2.y * t0.w * v0.w);
+                    o.z = pack_bf16(d.x * t1.x * v1.x, d.y * t1.y * v1.y);
+                    o.w = pack_bf16(e.x * t1.z * v1.z, e.y * t1.w * v1.w);
+                    *sp = o;
+                }
+                fence_proxy_async_smem();
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (leader) {
+                mbar_arrive(x_ready);
+                for (int cb = 0; cb < nbc; ++cb)
+                    tma_store_3d(&mapXg, smem + lay.x_off + (size_t)cb * 16384, cb * 64, row0, b);
+                tma_store_commit();
+                tma_store_wait_read0();
+                mbar_arrive(x_empty);
+            }
+            ph ^= 1;
+        }
+        if (leader) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+struct LaunchGcn {
+    CUtensorMap mapX, mapXg, mapW, mapY;
+    Params prm;
+    double flops = 0, bytes = 0;
+};
+
+inline int pick_wstages(int Cin, int C) {
+    const int cand[3] = {4, 3, 2};
+    for (int s : cand)
+        if (smem_layout(Cin, C, s).total <= 227u * 1024u) return s;
+    return 0;
+}
+
+inline int launch(Ctx *ctx, int kid, LaunchGcn &L, cudaStream_t st) {
+    const int ws = pick_wstages(L.prm.Cin, L.prm.C);
+    if (!ws) {
+        set_error("gcn_fused: shared memory plan does not fit (Cin=%d C=%d)", L.prm.Cin, L.prm.C);
+        return GS_ERR_UNSUPPORTED;
+    }
+    L.prm.wstages = ws;
+    const Smem lay = smem_layout(L.prm.Cin, L.prm.C, ws);
+    int grid = L.prm.ntiles < ctx->sm_count ? L.prm.ntiles : ctx->sm_count;
+    if (grid < 1) return GS_OK;
+#define GS_GCN_LAUNCH(S)                                                                                     \
+    do {                                                                                                     \
+        GS_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)lay.total));                                                       \
+        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);                                                      \
+        gcn_fused_kernel<S><<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.prm);   \
+    } while (0)
+    if (ws == 4) GS_GCN_LAUNCH(4);
+    else if (ws == 3) GS_GCN_LAUNCH(3);
+    else GS_GCN_LAUNCH(2);
+#undef GS_GCN_LAUNCH
+    GS_KERNEL_CHECK();
+    return GS_OK;
+}
+
+}  // namespace gcn
+}  // namespace gs

@@ -14,11 +14,14 @@
 // Stages replaced: /root/reference/README.md:27-34.
 #include "segment_common.cuh"
 #include "tc_gemm.cuh"
+#include "gcn_fused.cuh"
+#include <stdlib.h>
 
 namespace gs {
 
 struct BlockMaps {
     CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
+    CUtensorMap f_x_load, f_xg_store, f_y_store;    // fused GCN kernel (7-frame tiles)
     CUtensorMap wg, w1, w2, wr;
 };
 
@@ -27,6 +30,8 @@ struct Bf16Path {
     std::vector<float *> bias_t;                        // b2 (+ br)
     std::vector<BlockMaps> maps;
     int maps_T = -1;
+    bool fused_gcn = true;      // GOLFER_GCN_UNFUSED=1 selects the SIMT-aggregate + dense-GEMM pair
+    bool debug_xa = false;      // GOLFER_DEBUG_XA=1 dumps the fused kernel's XA chunks into bufXA
 };
 
 namespace {
@@ -106,6 +111,9 @@ int build_maps(Ctx *ctx, int T) {
         if (i > 0) {
             if ((rc = tc::make_act_map(&m.xa_in, ctx->bufXA, 3 * cin, rows, batch, 64, tc::kTileM))) return rc;
             if ((rc = tc::make_weight_map(&m.wg, bp->WgT[i], 3 * cin, C, 64, C))) return rc;
+            if ((rc = tc::make_act_map(&m.f_x_load, ctx->bufU[(i - 1) & 1], cin, rows, batch, 64, tc::kTileM))) return rc;
+            if ((rc = tc::make_act_map(&m.f_xg_store, ctx->bufX, cin, rows, batch, 64, gcn::kRowsPerTile))) return rc;
+            if ((rc = tc::make_act_map(&m.f_y_store, ctx->bufY, C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
             if (b.has_res) {
                 if ((rc = tc::make_act_map(&m.xg_in, ctx->bufX, cin, rows, batch, cr, tc::kTileM))) return rc;
                 if ((rc = tc::make_weight_map(&m.wr, bp->WrT[i], cin, C, cr, C))) return rc;
@@ -181,6 +189,8 @@ int bf16_path_create(Ctx *ctx) {
     }
     Bf16Path *bp = new Bf16Path();
     ctx->bf16 = bp;
+    if (const char *e = getenv("GOLFER_GCN_UNFUSED")) bp->fused_gcn = !(e[0] == '1');
+    if (const char *e = getenv("GOLFER_DEBUG_XA")) bp->debug_xa = (e[0] == '1');
     const size_t nb = ctx->blocks.size();
     bp->WgT.assign(nb, nullptr);
     bp->W1T.assign(nb, nullptr);
@@ -272,6 +282,28 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
                     skel, ctx->in_scale, ctx->in_shift, b.A, b.Wg, b.bg, b.Wr, b.br, cin, C, nframes, Y, R0);
             }
             GS_KERNEL_CHECK();
+        } else if (bp->fused_gcn) {
+            gcn::LaunchGcn L{};
+            L.mapX = m.f_x_load;
+            L.mapXg = m.f_xg_store;
+            L.mapW = m.wg;
+            L.mapY = m.f_y_store;
+            gcn::Params &q = L.prm;
+            q.Cin = cin;
+            q.C = C;
+            q.T = T;
+            q.B = B;
+            q.rows_per_clip = T * V17;
+            q.mtiles = cdiv(T, gcn::kFramesPerTile);
+            q.ntiles = B * q.mtiles;
+            q.gT = ctx->gT;
+            q.gV = ctx->gV;
+            q.A = b.A;
+            q.bias = b.bg;
+            q.dbg_xa = (bp->debug_xa && cin * 128 <= 119 * 256) ? XA : nullptr;
+            L.flops = 2.0 * rows * (V17 * 3.0 * cin + 3.0 * cin * C);
+            L.bytes = 2.0 * rows * (2.0 * cin + C);
+            if ((rc = gcn::launch(ctx, K_B_GEMM_GCN, L, st))) return rc;
         } else {
             const size_t items = nframes * cin;
             size_t g = (items + 255) / 256;
