@@ -18,9 +18,12 @@
 // TMEM map (512 columns): [0,C) acc | [256,320) D1 | [320,512) Abig_0..2.
 //
 // Warp roles (384 threads, persistent, 1 CTA/SM):
-//   w0 X-tile TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
+//   w0 input-box TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
 //   w4-7  TMEM warps: build Abig (once), convert D1 -> XA chunks, epilogue (bias, ReLU, TMA store)
-//   w8-11 gate warps: multiply the landed tile by gT*gV in place, TMA-store it as Xg
+//   w8-11 gate warps: multiply each landed box by gT*gV in place, TMA-store it as Xg
+// The input tile moves through a RING of 64-channel boxes (X box + its gT / gV slices, all three
+// brought by TMA); a box is released after its three MMA1s (chunk order: box-major, partition
+// minor), so the next tile's boxes load and get gated while this tile is still in the MMAs.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -39,7 +42,7 @@ struct Params {
     int Cin, C, T, B;
     int mtiles, ntiles, rows_per_clip;
     int wstages;
-    const float *gT;      // [B,T,Cin]   (nullptr: no gating)
+    const float *gT;      // [B,T,Cin]   (only used to decide whether gating is on)
     const float *gV;      // [B,17,Cin]
     const float *A;       // [3,17,17] fp32
     const float *bias;    // [C]
@@ -86,13 +89,20 @@ __device__ __forceinline__ uint32_t make_idesc_agg() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
+constexpr int kXSlots = 4;                       // input-box ring depth
+constexpr uint32_t kGtOff = 16384;               // slot: [X box 16 KB | gT 8x64 fp32 | gV 17x64 fp32]
+constexpr uint32_t kGvOff = 16384 + 2048;
+constexpr uint32_t kSlotBytes = 23552;           // 23 KB, keeps every X box 1024 B aligned
+constexpr uint32_t kSlotTx = 16384 + 2048 + 17 * 256;
+
 struct Smem {
     uint32_t x_off, w_off, xa_off, bar_off, total, w_stage_bytes;
 };
 __host__ __device__ inline Smem smem_layout(int Cin, int C, int wstages) {
     Smem s;
+    (void)Cin;
     s.x_off = 0;
-    s.w_off = (uint32_t)(Cin / 64) * 16384u;
+    s.w_off = (uint32_t)kXSlots * kSlotBytes;
     s.w_stage_bytes = (uint32_t)C * 128u;
     s.xa_off = s.w_off + s.w_stage_bytes * wstages;
     s.bar_off = s.xa_off + 2u * 16384u;
@@ -109,18 +119,21 @@ template <int WSTAGES>
 __global__ void __launch_bounds__(kThreadsGcn, 1)
 gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXg,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
+                 const __grid_constant__ CUtensorMap mapGT, const __grid_constant__ CUtensorMap mapGV,
                  const __grid_constant__ Params prm) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const Smem lay = smem_layout(prm.Cin, prm.C, WSTAGES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar_off);
-    uint64_t *x_full = bars + 0, *x_ready = bars + 1, *x_empty = bars + 2;
-    uint64_t *d1_full = bars + 3, *d1_empty = bars + 4;
-    uint64_t *xa_full = bars + 5;    // [2]
-    uint64_t *xa_empty = bars + 7;   // [2]
-    uint64_t *acc_full = bars + 9, *acc_empty = bars + 10;
-    uint64_t *w_full = bars + 11;              // [WSTAGES]
+    uint64_t *x_full = bars + 0;                 // [kXSlots]
+    uint64_t *x_ready = bars + kXSlots;          // [kXSlots]
+    uint64_t *x_empty = bars + 2 * kXSlots;      // [kXSlots]
+    uint64_t *d1_full = bars + 3 * kXSlots, *d1_empty = d1_full + 1;
+    uint64_t *xa_full = d1_full + 2;    // [2]
+    uint64_t *xa_empty = d1_full + 4;   // [2]
+    uint64_t *acc_full = d1_full + 6, *acc_empty = d1_full + 7;
+    uint64_t *w_full = d1_full + 8;            // [WSTAGES]
     uint64_t *w_empty = w_full + WSTAGES;      // [WSTAGES]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_empty + WSTAGES);
 
@@ -134,11 +147,15 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         tma_prefetch_desc(&mapXg);
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapGT);
+        tma_prefetch_desc(&mapGV);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(x_full, 1);
-        mbar_init(x_ready, 1);
-        mbar_init(x_empty, 2);          // MMA1 commit + Xg store drained
+        for (int s = 0; s < kXSlots; ++s) {
+            mbar_init(&x_full[s], 1);
+            mbar_init(&x_ready[s], 1);
+            mbar_init(&x_empty[s], 2);  // MMA1 commit + Xg store drained
+        }
         mbar_init(d1_full, 1);
         mbar_init(d1_empty, 128);
         for (int s = 0; s < 2; ++s) {
@@ -188,21 +205,27 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     tc_fence_after();
 
     if (warp == 0) {
-        // ===== X-tile producer =====
+        // ===== input-box producer: X box + its gT / gV slices per ring slot =====
         if (lane == 0) {
+            int slot = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
                 const int b = tile / prm.mtiles;
-                const int row0 = (tile % prm.mtiles) * kRowsPerTile;
-                mbar_wait(x_empty, ph ^ 1);
-                mbar_expect_tx(x_full, (uint32_t)nbc * 16384u);
-                for (int cb = 0; cb < nbc; ++cb)
-                    tma_load_3d(smem + lay.x_off + (size_t)cb * 16384, &mapX, x_full, cb * 64, row0, b);
-                ph ^= 1;
+                const int mt = tile % prm.mtiles;
+                const int row0 = mt * kRowsPerTile;
+                for (int cb = 0; cb < nbc; ++cb) {
+                    unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
+                    mbar_wait(&x_empty[slot], ph ^ 1);
+                    mbar_expect_tx(&x_full[slot], kSlotTx);
+                    tma_load_3d(sl, &mapX, &x_full[slot], cb * 64, row0, b);
+                    tma_load_2d(sl + kGtOff, &mapGT, &x_full[slot], cb * 64, b * prm.T + mt * kFramesPerTile);
+                    tma_load_2d(sl + kGvOff, &mapGV, &x_full[slot], cb * 64, b * 17);
+                    if (++slot == kXSlots) { slot = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 3) {
-        // ===== weight-ring producer: chunk q of every tile is WgT[:, q*64 .. q*64+64) =====
+        // ===== weight-ring producer: chunk q = (box cb, partition p) needs WgT[:, p*Cin + cb*64 ..) =====
         if (lane == 0) {
             int stage = 0;
             uint32_t ph = 0;
@@ -210,7 +233,8 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 for (int q = 0; q < nq; ++q) {
                     mbar_wait(&w_empty[stage], ph ^ 1);
                     mbar_expect_tx(&w_full[stage], lay.w_stage_bytes);
-                    tma_load_2d(smem + lay.w_off + (size_t)stage * lay.w_stage_bytes, &mapW, &w_full[stage], q * 64, 0);
+                    tma_load_2d(smem + lay.w_off + (size_t)stage * lay.w_stage_bytes, &mapW, &w_full[stage],
+                                (q % 3) * Cin + (q / 3) * 64, 0);
                     if (++stage == WSTAGES) { stage = 0; ph ^= 1; }
                 }
             }
@@ -242,14 +266,18 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 ++xa_cnt;
                 if (++wstage == WSTAGES) { wstage = 0; wph ^= 1; }
             };
+            int xslot = 0;
+            uint32_t xph = 0;
             for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-                mbar_wait(x_ready, tile_ph);
-                tc_fence_after();
                 for (int q = 0; q < nq; ++q) {
-                    const int p = q / nbc, cb = q % nbc;
+                    const int p = q % 3;
+                    if (p == 0) {
+                        mbar_wait(&x_ready[xslot], xph);      // box gated and visible to the async proxy
+                        tc_fence_after();
+                    }
                     mbar_wait(d1_empty, (d1_cnt & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)cb * 16384);
+                    const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)xslot * kSlotBytes);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         // 16 input rows per step: +8 TMEM columns of Abig, +2048 B (two 8-row groups) of X
@@ -258,7 +286,10 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     }
                     umma_commit(d1_full);
                     ++d1_cnt;
-                    if (q == nq - 1) umma_commit(x_empty);     // every MMA1 of this tile has read X
+                    if (p == 2) {                              // all three MMA1s of this box issued
+                        umma_commit(&x_empty[xslot]);
+                        if (++xslot == kXSlots) { xslot = 0; xph ^= 1; }
+                    }
                     if (q > 0) issue_mma2(q - 1);
                 }
                 issue_mma2(nq - 1);
@@ -349,50 +380,51 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         }
         if (leader) tma_store_wait_all0();
     } else if (warp >= 8) {
-        // ===== gate warps: Xg = X * gT * gV in place, then TMA-store Xg =====
+        // ===== gate warps: Xg = X * gT * gV in place (gates read from the slot), TMA-store Xg =====
         const int gt_id = threadIdx.x - 256;          // 0..127
         const bool leader = (gt_id == 0);
-        const int cpr = Cin / 8;                      // 16-byte chunks per row
+        int slot = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
             const int b = tile / prm.mtiles;
             const int row0 = (tile % prm.mtiles) * kRowsPerTile;
-            mbar_wait(x_full, ph);
-            if (prm.gT) {
-                for (int idx = gt_id; idx < kTileM * cpr; idx += 128) {
-                    const int r = idx / cpr, ch = idx % cpr;
-                    const int grow = row0 + r;
-                    if (grow >= prm.rows_per_clip) continue;     // TMA zero-filled
-                    const int t = grow / 17, v = grow % 17;
-                    const int cb = ch >> 3, cc = ch & 7;
-                    uint4 *sp = reinterpret_cast<uint4 *>(smem + lay.x_off + (size_t)cb * 16384 + (size_t)r * 128 +
-                                                          ((cc ^ (r & 7)) << 4));
-                    uint4 x = *sp;
-                    const float4 *gt = reinterpret_cast<const float4 *>(prm.gT + ((size_t)b * prm.T + t) * Cin + ch * 8);
-                    const float4 *gv = reinterpret_cast<const float4 *>(prm.gV + ((size_t)b * 17 + v) * Cin + ch * 8);
-                    const float4 t0 = __ldg(gt), t1 = __ldg(gt + 1), v0 = __ldg(gv), v1 = __ldg(gv + 1);
-                    const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
-                    const float2 a = __bfloat1622float2(xp[0]), c2 = __bfloat1622float2(xp[1]);
-                    const float2 d = __bfloat1622float2(xp[2]), e = __bfloat1622float2(xp[3]);
-                    uint4 o;
-                    o.x = pack_bf16(a.x * t0.x * v0.x, a.y * t0.y * v0.y);
-                    o.y = pack_bf16(c2.x * t0.z * v0.z, c2.y * t0.w * v0.w);
-                    o.z = pack_bf16(d.x * t1.x * v1.x, d.y * t1.y * v1.y);
-                    o.w = pack_bf16(e.x * t1.z * v1.z, e.y * t1.w * v1.w);
-                    *sp = o;
+            for (int cb = 0; cb < nbc; ++cb) {
+                unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
+                mbar_wait(&x_full[slot], ph);
+                if (prm.gT) {
+                    const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][64]
+                    const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][64]
+#pragma unroll 2
+                    for (int idx = gt_id; idx < kTileM * 8; idx += 128) {
+                        const int r = idx >> 3, cc = idx & 7;
+                        if (row0 + r >= prm.rows_per_clip) continue;     // TMA zero-filled rows
+                        const int f = r / 17, v = r - f * 17;
+                        uint4 *sp = reinterpret_cast<uint4 *>(sl + (size_t)r * 128 + ((cc ^ (r & 7)) << 4));
+                        const uint4 x = *sp;
+                        const float4 t0 = sgt[f * 16 + cc * 2], t1 = sgt[f * 16 + cc * 2 + 1];
+                        const float4 v0 = sgv[v * 16 + cc * 2], v1 = sgv[v * 16 + cc * 2 + 1];
+                        const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
+                        const float2 a = __bfloat1622float2(xp[0]), c2 = __bfloat1622float2(xp[1]);
+                        const float2 d = __bfloat1622float2(xp[2]), e = __bfloat1622float2(xp[3]);
+                        uint4 o;
+                        o.x = pack_bf16(a.x * t0.x * v0.x, a.y * t0.y * v0.y);
+                        o.y = pack_bf16(c2.x * t0.z * v0.z, c2.y * t0.w * v0.w);
+                        o.z = pack_bf16(d.x * t1.x * v1.x, d.y * t1.y * v1.y);
+                        o.w = pack_bf16(e.x * t1.z * v1.z, e.y * t1.w * v1.w);
+                        *sp = o;
+                    }
+                    fence_proxy_async_smem();
                 }
-                fence_proxy_async_smem();
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (leader) {
+                    mbar_arrive(&x_ready[slot]);
+                    tma_store_3d(&mapXg, sl, cb * 64, row0, b);
+                    tma_store_commit();
+                    tma_store_wait_read0();
+                    mbar_arrive(&x_empty[slot]);
+                }
+                if (++slot == kXSlots) { slot = 0; ph ^= 1; }
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (leader) {
-                mbar_arrive(x_ready);
-                for (int cb = 0; cb < nbc; ++cb)
-                    tma_store_3d(&mapXg, smem + lay.x_off + (size_t)cb * 16384, cb * 64, row0, b);
-                tma_store_commit();
-                tma_store_wait_read0();
-                mbar_arrive(x_empty);
-            }
-            ph ^= 1;
         }
         if (leader) tma_store_wait_all0();
     }
@@ -405,7 +437,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 }
 
 struct LaunchGcn {
-    CUtensorMap mapX, mapXg, mapW, mapY;
+    CUtensorMap mapX, mapXg, mapW, mapY, mapGT, mapGV;
     Params prm;
     double flops = 0, bytes = 0;
 };
@@ -432,7 +464,8 @@ inline int launch(Ctx *ctx, int kid, LaunchGcn &L, cudaStream_t st) {
         GS_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)lay.total));                                                       \
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);                                                      \
-        gcn_fused_kernel<S><<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.prm);   \
+        gcn_fused_kernel<S><<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT,  \
+                                                                  L.mapGV, L.prm);                          \
     } while (0)
     if (ws == 4) GS_GCN_LAUNCH(4);
     else if (ws == 3) GS_GCN_LAUNCH(3);

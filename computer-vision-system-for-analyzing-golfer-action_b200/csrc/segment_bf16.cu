@@ -21,7 +21,7 @@ namespace gs {
 
 struct BlockMaps {
     CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
-    CUtensorMap f_x_load, f_xg_store, f_y_store;    // fused GCN kernel (7-frame tiles)
+    CUtensorMap f_x_load, f_xg_store, f_y_store, f_gt, f_gv;    // fused GCN kernel (7-frame tiles)
     CUtensorMap wg, w1, w2, wr;
 };
 
@@ -114,6 +114,8 @@ int build_maps(Ctx *ctx, int T) {
             if ((rc = tc::make_act_map(&m.f_x_load, ctx->bufU[(i - 1) & 1], cin, rows, batch, 64, tc::kTileM))) return rc;
             if ((rc = tc::make_act_map(&m.f_xg_store, ctx->bufX, cin, rows, batch, 64, gcn::kRowsPerTile))) return rc;
             if ((rc = tc::make_act_map(&m.f_y_store, ctx->bufY, C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
+            if ((rc = tc::make_f32_map(&m.f_gt, ctx->gT, cin, (long long)batch * T, 64, 8))) return rc;
+            if ((rc = tc::make_f32_map(&m.f_gv, ctx->gV, cin, (long long)batch * V17, 64, V17))) return rc;
             if (b.has_res) {
                 if ((rc = tc::make_act_map(&m.xg_in, ctx->bufX, cin, rows, batch, cr, tc::kTileM))) return rc;
                 if ((rc = tc::make_weight_map(&m.wr, bp->WrT[i], cin, C, cr, C))) return rc;
@@ -288,6 +290,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             L.mapXg = m.f_xg_store;
             L.mapW = m.wg;
             L.mapY = m.f_y_store;
+            L.mapGT = m.f_gt;
+            L.mapGV = m.f_gv;
             gcn::Params &q = L.prm;
             q.Cin = cin;
             q.C = C;

@@ -448,6 +448,27 @@ inline int make_weight_map(CUtensorMap *m, const void *base, int kwidth, int nro
     return GS_OK;
 }
 
+// fp32 [nrows, width] matrix -> 2-D map, box (box_w, box_rows), no swizzle (gate slices)
+inline int make_f32_map(CUtensorMap *m, const void *base, int width, long long nrows, int box_w, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return GS_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)width * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(f32 %dx%lld box %dx%d) failed: %d", width, nrows, box_w, box_rows, (int)r);
+        return GS_ERR_CUDA;
+    }
+    return GS_OK;
+}
+
 struct Launch {
     CUtensorMap mapA0, mapA1, mapB0, mapB1, mapOut;
     Program prog;
