@@ -493,6 +493,16 @@ int gs_compare(gs_ctx *h, const float *a_dev, const float *b_dev, const int32_t 
                           (cudaStream_t)cuda_stream);
 }
 
+int gs_debug_read(gs_ctx *h, const char *name, void *host_out, size_t nbytes) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || !name || !host_out) {
+        set_error("bad gs_debug_read arguments");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return bf16_debug_read(ctx, name, host_out, nbytes);
+}
+
 int gs_profile_enable(gs_ctx *h, int on) {
     Ctx *ctx = (Ctx *)h;
     if (!ctx) return GS_ERR_INVALID;

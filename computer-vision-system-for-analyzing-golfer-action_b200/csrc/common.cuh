@@ -166,6 +166,7 @@ int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
 // segment_bf16.cu
 int bf16_path_create(Ctx *ctx);
 void bf16_path_destroy(Ctx *ctx);
+int bf16_debug_read(Ctx *ctx, const char *name, void *host, size_t nbytes);
 int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,
                          int upto_block, float *feat_out, cudaStream_t st);
 

@@ -11,16 +11,18 @@
 // tcgen05 tensor cores:
 //   MMA1 (TS form)  D1[128 x 64]  = Abig_p[128 x 128] . Xg[128 rows x 64 ch]
 //        Abig_p = I_7 (x) A_p, the block-diagonal adjacency, lives in TENSOR MEMORY as the
-//        A operand (bf16, 64 columns per partition); Xg is the TMA-loaded tile itself, used
+//        A operand (bf16, 64 columns per partition); Xg is the TMA-loaded box itself, used
 //        in place as an MN-major B operand (channels contiguous).
 //   convert         D1 (fp32, TMEM) -> bf16 -> 128B-swizzled K-major smem chunk
 //   MMA2 (SS form)  acc[128 x C] += XAchunk[128 x 64] . WgT[C x 64]^T     (TMA weight ring)
-// TMEM map (512 columns): [0,C) acc | [256,320) D1 | [320,512) Abig_0..2.
+// TMEM map (512 columns): accumulator(s) from column 0 (two of them when 2C <= 256),
+// [256,320) D1, [320,512) Abig_0..2.
 //
-// Warp roles (384 threads, persistent, 1 CTA/SM):
+// Warp roles (512 threads, persistent, 1 CTA/SM):
 //   w0 input-box TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
-//   w4-7  TMEM warps: build Abig (once), convert D1 -> XA chunks, epilogue (bias, ReLU, TMA store)
-//   w8-11 gate warps: multiply each landed box by gT*gV in place, TMA-store it as Xg
+//   w4-7   convert warps : build Abig (once), D1 -> bf16 XA chunks
+//   w8-11  gate warps    : multiply each landed box by gT*gV in place, TMA-store it as Xg
+//   w12-15 epilogue warps: acc -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store of Y
 // The input tile moves through a RING of 64-channel boxes (X box + its gT / gV slices, all three
 // brought by TMA); a box is released after its three MMA1s (chunk order: box-major, partition
 // minor), so the next tile's boxes load and get gated while this tile is still in the MMAs.
@@ -32,22 +34,36 @@ namespace gcn {
 
 using namespace tc;
 
-constexpr int kThreadsGcn = 384;
+constexpr int kThreadsGcn = 512;
 constexpr int kFramesPerTile = 7;
 constexpr int kRowsPerTile = kFramesPerTile * 17;   // 119
 constexpr int kColD1 = 256;
 constexpr int kColAbig = 320;
+constexpr int kMaxXSlots = 8, kMaxWStages = 4;
+constexpr uint32_t kGtOff = 16384;               // slot: [X box 16 KB | gT 8x64 fp32 | gV 17x64 fp32]
+constexpr uint32_t kGvOff = 16384 + 2048;
+constexpr uint32_t kSlotBytes = 23552;           // 23 KB, keeps every X box 1024 B aligned
+constexpr uint32_t kSlotTx = 16384 + 2048 + 17 * 256;
 
 struct Params {
     int Cin, C, T, B;
     int mtiles, ntiles, rows_per_clip;
-    int wstages;
-    const float *gT;      // [B,T,Cin]   (only used to decide whether gating is on)
+    int xslots, wstages, eslots, nacc;
+    const float *gT;      // [B,T,Cin]   (maps carry the data; non-null = gating on)
     const float *gV;      // [B,17,Cin]
     const float *A;       // [3,17,17] fp32
     const float *bias;    // [C]
-    __nv_bfloat16 *dbg_xa;   // optional [ntiles*128, 3*Cin] dump of the converted XA chunks
+    __nv_bfloat16 *dbg_xa;       // optional [ntiles*128, 3*Cin] dump of the converted XA chunks
+    unsigned long long *trace;   // optional clock64 trace of CTA 0 (tools/trace_gcn.py)
 };
+
+// trace layout: [role 0..4][tile 0..kTraceTiles)[event 0..kTraceEv)
+constexpr int kTraceTiles = 6, kTraceEv = 64;
+#define GCN_TRACE(role, tcount, ev)                                                                     \
+    do {                                                                                                \
+        if (prm.trace && blockIdx.x == 0 && (tcount) < kTraceTiles && (ev) < kTraceEv)                  \
+            prm.trace[((role)*kTraceTiles + (tcount)) * kTraceEv + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -89,23 +105,17 @@ __device__ __forceinline__ uint32_t make_idesc_agg() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-constexpr int kXSlots = 4;                       // input-box ring depth
-constexpr uint32_t kGtOff = 16384;               // slot: [X box 16 KB | gT 8x64 fp32 | gV 17x64 fp32]
-constexpr uint32_t kGvOff = 16384 + 2048;
-constexpr uint32_t kSlotBytes = 23552;           // 23 KB, keeps every X box 1024 B aligned
-constexpr uint32_t kSlotTx = 16384 + 2048 + 17 * 256;
-
 struct Smem {
-    uint32_t x_off, w_off, xa_off, bar_off, total, w_stage_bytes;
+    uint32_t x_off, w_off, xa_off, epi_off, bar_off, total, w_stage_bytes;
 };
-__host__ __device__ inline Smem smem_layout(int Cin, int C, int wstages) {
+__host__ __device__ inline Smem smem_layout(int C, int xslots, int wstages, int eslots) {
     Smem s;
-    (void)Cin;
     s.x_off = 0;
-    s.w_off = (uint32_t)kXSlots * kSlotBytes;
+    s.w_off = (uint32_t)xslots * kSlotBytes;
     s.w_stage_bytes = (uint32_t)C * 128u;
     s.xa_off = s.w_off + s.w_stage_bytes * wstages;
-    s.bar_off = s.xa_off + 2u * 16384u;
+    s.epi_off = s.xa_off + 2u * 16384u;
+    s.bar_off = s.epi_off + (uint32_t)eslots * 16384u;
     s.total = s.bar_off + 512 + 1024;
     return s;
 }
@@ -115,7 +125,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int WSTAGES>
 __global__ void __launch_bounds__(kThreadsGcn, 1)
 gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXg,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
@@ -124,18 +133,20 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    const Smem lay = smem_layout(prm.Cin, prm.C, WSTAGES);
+    const int XS = prm.xslots, WS = prm.wstages, ES = prm.eslots, NACC = prm.nacc;
+    const Smem lay = smem_layout(prm.C, XS, WS, ES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar_off);
-    uint64_t *x_full = bars + 0;                 // [kXSlots]
-    uint64_t *x_ready = bars + kXSlots;          // [kXSlots]
-    uint64_t *x_empty = bars + 2 * kXSlots;      // [kXSlots]
-    uint64_t *d1_full = bars + 3 * kXSlots, *d1_empty = d1_full + 1;
-    uint64_t *xa_full = d1_full + 2;    // [2]
-    uint64_t *xa_empty = d1_full + 4;   // [2]
-    uint64_t *acc_full = d1_full + 6, *acc_empty = d1_full + 7;
-    uint64_t *w_full = d1_full + 8;            // [WSTAGES]
-    uint64_t *w_empty = w_full + WSTAGES;      // [WSTAGES]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_empty + WSTAGES);
+    uint64_t *x_full = bars;                          // [kMaxXSlots]
+    uint64_t *x_ready = x_full + kMaxXSlots;          // [kMaxXSlots]
+    uint64_t *x_empty = x_ready + kMaxXSlots;         // [kMaxXSlots]
+    uint64_t *w_full = x_empty + kMaxXSlots;          // [kMaxWStages]
+    uint64_t *w_empty = w_full + kMaxWStages;         // [kMaxWStages]
+    uint64_t *d1_full = w_empty + kMaxWStages, *d1_empty = d1_full + 1;
+    uint64_t *xa_full = d1_full + 2;                  // [2]
+    uint64_t *xa_empty = d1_full + 4;                 // [2]
+    uint64_t *acc_full = d1_full + 6;                 // [2]
+    uint64_t *acc_empty = d1_full + 8;                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_full + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Cin = prm.Cin, C = prm.C;
@@ -151,22 +162,22 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         tma_prefetch_desc(&mapGV);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kXSlots; ++s) {
+        for (int s = 0; s < kMaxXSlots; ++s) {
             mbar_init(&x_full[s], 1);
             mbar_init(&x_ready[s], 1);
-            mbar_init(&x_empty[s], 2);  // MMA1 commit + Xg store drained
+            mbar_init(&x_empty[s], 2);      // MMA1 commit + Xg store drained
+        }
+        for (int s = 0; s < kMaxWStages; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
         }
         mbar_init(d1_full, 1);
         mbar_init(d1_empty, 128);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&xa_full[s], 128);
             mbar_init(&xa_empty[s], 1);
-        }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 128);
-        for (int s = 0; s < WSTAGES; ++s) {
-            mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 1);
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
         }
         fence_barrier_init();
     }
@@ -207,20 +218,21 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     if (warp == 0) {
         // ===== input-box producer: X box + its gT / gV slices per ring slot =====
         if (lane == 0) {
-            int slot = 0;
+            int slot = 0, tcount = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
                 const int b = tile / prm.mtiles;
                 const int mt = tile % prm.mtiles;
                 const int row0 = mt * kRowsPerTile;
                 for (int cb = 0; cb < nbc; ++cb) {
                     unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
                     mbar_wait(&x_empty[slot], ph ^ 1);
+                    GCN_TRACE(0, tcount, cb);
                     mbar_expect_tx(&x_full[slot], kSlotTx);
                     tma_load_3d(sl, &mapX, &x_full[slot], cb * 64, row0, b);
                     tma_load_2d(sl + kGtOff, &mapGT, &x_full[slot], cb * 64, b * prm.T + mt * kFramesPerTile);
                     tma_load_2d(sl + kGvOff, &mapGV, &x_full[slot], cb * 64, b * 17);
-                    if (++slot == kXSlots) { slot = 0; ph ^= 1; }
+                    if (++slot == XS) { slot = 0; ph ^= 1; }
                 }
             }
         }
@@ -235,7 +247,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     mbar_expect_tx(&w_full[stage], lay.w_stage_bytes);
                     tma_load_2d(smem + lay.w_off + (size_t)stage * lay.w_stage_bytes, &mapW, &w_full[stage],
                                 (q % 3) * Cin + (q / 3) * 64, 0);
-                    if (++stage == WSTAGES) { stage = 0; ph ^= 1; }
+                    if (++stage == WS) { stage = 0; ph ^= 1; }
                 }
             }
         }
@@ -244,31 +256,33 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc_agg();
             const uint32_t idesc2 = make_idesc_bf16((uint32_t)C);
-            const uint32_t t_acc = tmem_base, t_d1 = tmem_base + kColD1, t_ab = tmem_base + kColAbig;
-            uint32_t tile_ph = 0;       // x_ready / acc_empty phase
+            const uint32_t t_d1 = tmem_base + kColD1, t_ab = tmem_base + kColAbig;
             uint32_t d1_cnt = 0;        // running count of D1 uses
             uint32_t xa_cnt = 0;        // running count of XA chunks consumed
-            int wstage = 0;
-            uint32_t wph = 0;
+            uint32_t acc_cnt = 0;       // running count of tiles (accumulator uses)
+            int wstage = 0, xslot = 0, tcount = 0;
+            uint32_t wph = 0, xph = 0;
             auto issue_mma2 = [&](int j) {
                 const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
-                if (j == 0) mbar_wait(acc_empty, tile_ph ^ 1);   // previous tile's epilogue has drained acc
+                const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
+                if (j == 0) mbar_wait(&acc_empty[as], aph ^ 1);   // epilogue has drained this accumulator
                 mbar_wait(&xa_full[slot], ph);
+                GCN_TRACE(1, tcount, 16 + j);
                 mbar_wait(&w_full[wstage], wph);
+                GCN_TRACE(1, tcount, 32 + j);
                 tc_fence_after();
                 const uint64_t da = make_kmajor_desc(smem_u32(smem + lay.xa_off + slot * 16384u), 128);
                 const uint64_t db = make_kmajor_desc(smem_u32(smem + lay.w_off + (size_t)wstage * lay.w_stage_bytes), 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16(t_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (uint32_t)((j > 0) | (k > 0)));
+                    umma_bf16(tmem_base + as * (uint32_t)C, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2,
+                              (uint32_t)((j > 0) | (k > 0)));
                 umma_commit(&xa_empty[slot]);
                 umma_commit(&w_empty[wstage]);
                 ++xa_cnt;
-                if (++wstage == WSTAGES) { wstage = 0; wph ^= 1; }
+                if (++wstage == WS) { wstage = 0; wph ^= 1; }
             };
-            int xslot = 0;
-            uint32_t xph = 0;
-            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
                 for (int q = 0; q < nq; ++q) {
                     const int p = q % 3;
                     if (p == 0) {
@@ -276,6 +290,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         tc_fence_after();
                     }
                     mbar_wait(d1_empty, (d1_cnt & 1) ^ 1);
+                    GCN_TRACE(1, tcount, q);
                     tc_fence_after();
                     const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)xslot * kSlotBytes);
 #pragma unroll
@@ -288,28 +303,27 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     ++d1_cnt;
                     if (p == 2) {                              // all three MMA1s of this box issued
                         umma_commit(&x_empty[xslot]);
-                        if (++xslot == kXSlots) { xslot = 0; xph ^= 1; }
+                        if (++xslot == XS) { xslot = 0; xph ^= 1; }
                     }
                     if (q > 0) issue_mma2(q - 1);
                 }
                 issue_mma2(nq - 1);
-                umma_commit(acc_full);
-                tile_ph ^= 1;
+                umma_commit(&acc_full[acc_cnt % (uint32_t)NACC]);
+                ++acc_cnt;
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        // ===== TMEM warps: convert D1 -> XA chunks, then the tile epilogue =====
+        // ===== convert warps: D1 (fp32, TMEM) -> bf16 XA chunk in swizzled smem =====
         const int ew = warp - 4;
         const int r = ew * 32 + lane;
-        const bool leader = (threadIdx.x == 128);
         const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-        uint32_t d1_cnt = 0, xa_cnt = 0, tile_ph = 0;
-        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-            const int b = tile / prm.mtiles;
-            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+        uint32_t d1_cnt = 0, xa_cnt = 0;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
             for (int q = 0; q < nq; ++q) {
                 uint32_t v[64];
                 mbar_wait(d1_full, d1_cnt & 1);
+                if (threadIdx.x == 128) GCN_TRACE(2, tcount, q);
                 tc_fence_after();
                 tmem_ld32(tmem_base + lane_base + kColD1, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                 tmem_ld32(tmem_base + lane_base + kColD1 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -319,6 +333,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 ++d1_cnt;
                 const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
                 mbar_wait(&xa_empty[slot], ph ^ 1);  // MMA2 that last read this slot has retired
+                if (threadIdx.x == 128) GCN_TRACE(2, tcount, 16 + q);
                 unsigned char *box = smem + lay.xa_off + slot * 16384u;
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
@@ -329,68 +344,28 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     pk.w = pack_bf16(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
                     *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
                     if (prm.dbg_xa)
-                        *reinterpret_cast<uint4 *>(prm.dbg_xa + ((size_t)tile * 128 + r) * (size_t)(3 * Cin) + q * 64 + cc * 8) = pk;
+                        *reinterpret_cast<uint4 *>(prm.dbg_xa + ((size_t)tile * 128 + r) * (size_t)(3 * Cin) +
+                                                   (q % 3) * Cin + (q / 3) * 64 + cc * 8) = pk;
                 }
                 fence_proxy_async_smem();
                 mbar_arrive(&xa_full[slot]);
+                if (threadIdx.x == 128) GCN_TRACE(2, tcount, 32 + q);
                 ++xa_cnt;
             }
-            // ---- epilogue: acc -> +bias, ReLU -> bf16 -> staging (the XA slots) -> TMA store ----
-            mbar_wait(acc_full, tile_ph);
-            tc_fence_after();
-            for (int qb = 0; qb < C / 64; ++qb) {
-                uint32_t v[64];
-                tmem_ld32(tmem_base + lane_base + (uint32_t)(qb * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld32(tmem_base + lane_base + (uint32_t)(qb * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                tmem_ld_wait();
-                if (qb == C / 64 - 1) {
-                    tc_fence_before();
-                    mbar_arrive(acc_empty);          // accumulator fully read
-                }
-                const int sb = qb & 1;
-                if (qb >= 2) {                        // staging slot reuse: its previous store must be drained
-                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
-                unsigned char *box = smem + lay.xa_off + sb * 16384u;
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        f[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + __ldg(prm.bias + qb * 64 + cc * 8 + e), 0.f);
-                    uint4 pk;
-                    pk.x = pack_bf16(f[0], f[1]);
-                    pk.y = pack_bf16(f[2], f[3]);
-                    pk.z = pack_bf16(f[4], f[5]);
-                    pk.w = pack_bf16(f[6], f[7]);
-                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
-                }
-                fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (leader) {
-                    tma_store_3d(&mapY, box, qb * 64, row0, b);
-                    tma_store_commit();
-                }
-            }
-            // the staging slots become XA slots again for the next tile
-            if (leader) tma_store_wait_read0();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            tile_ph ^= 1;
         }
-        if (leader) tma_store_wait_all0();
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ===== gate warps: Xg = X * gT * gV in place (gates read from the slot), TMA-store Xg =====
         const int gt_id = threadIdx.x - 256;          // 0..127
         const bool leader = (gt_id == 0);
-        int slot = 0;
+        int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
             const int b = tile / prm.mtiles;
             const int row0 = (tile % prm.mtiles) * kRowsPerTile;
             for (int cb = 0; cb < nbc; ++cb) {
                 unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
                 mbar_wait(&x_full[slot], ph);
+                if (leader) GCN_TRACE(3, tcount, cb);
                 if (prm.gT) {
                     const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][64]
                     const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][64]
@@ -418,13 +393,81 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (leader) {
                     mbar_arrive(&x_ready[slot]);
+                    GCN_TRACE(3, tcount, 16 + cb);
                     tma_store_3d(&mapXg, sl, cb * 64, row0, b);
                     tma_store_commit();
-                    tma_store_wait_read0();
-                    mbar_arrive(&x_empty[slot]);
+                    // the PREVIOUS box's store has been in flight for a whole box period: drain it now
+                    // and release its slot (deferred wait keeps the gate pipeline moving)
+                    if (prev_slot >= 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        mbar_arrive(&x_empty[prev_slot]);
+                    }
+                    prev_slot = slot;
                 }
-                if (++slot == kXSlots) { slot = 0; ph ^= 1; }
+                if (++slot == XS) { slot = 0; ph ^= 1; }
             }
+        }
+        if (leader) {
+            tma_store_wait_read0();
+            if (prev_slot >= 0) mbar_arrive(&x_empty[prev_slot]);
+            tma_store_wait_all0();
+        }
+    } else if (warp >= 12) {
+        // ===== epilogue warps: acc -> +bias, ReLU -> bf16 -> staging ring -> TMA store =====
+        const int ew = warp - 12;
+        const int r = ew * 32 + lane;
+        const bool leader = (threadIdx.x == 384);
+        const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+        uint32_t acc_cnt = 0, ecnt = 0;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
+            const int b = tile / prm.mtiles;
+            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+            const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
+            mbar_wait(&acc_full[as], aph);
+            if (leader) GCN_TRACE(4, tcount, 0);
+            tc_fence_after();
+            for (int qb = 0; qb < C / 64; ++qb) {
+                uint32_t v[64];
+                const uint32_t ta = tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64);
+                tmem_ld32(ta, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                if (qb == C / 64 - 1) {
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[as]);     // accumulator fully read
+                }
+                const uint32_t es = ecnt % (uint32_t)ES;
+                // staging slot reuse: the store issued ES boxes ago must have finished reading it
+                if (leader && ecnt >= (uint32_t)ES) {
+                    if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                unsigned char *box = smem + lay.epi_off + es * 16384u;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        f[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + __ldg(prm.bias + qb * 64 + cc * 8 + e), 0.f);
+                    uint4 pk;
+                    pk.x = pack_bf16(f[0], f[1]);
+                    pk.y = pack_bf16(f[2], f[3]);
+                    pk.z = pack_bf16(f[4], f[5]);
+                    pk.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    tma_store_3d(&mapY, box, qb * 64, row0, b);
+                    tma_store_commit();
+                }
+                ++ecnt;
+            }
+            if (leader) GCN_TRACE(4, tcount, 1);
+            ++acc_cnt;
         }
         if (leader) tma_store_wait_all0();
     }
@@ -442,35 +485,39 @@ struct LaunchGcn {
     double flops = 0, bytes = 0;
 };
 
-inline int pick_wstages(int Cin, int C) {
-    const int cand[3] = {4, 3, 2};
-    for (int s : cand)
-        if (smem_layout(Cin, C, s).total <= 227u * 1024u) return s;
-    return 0;
+// Largest rings that fit 227 KB: epilogue staging, then the weight ring (latency of the L2
+// stream), then as many input boxes as remain (at least 3).
+inline bool plan_smem(Params &p) {
+    p.nacc = (2 * p.C <= 256) ? 2 : 1;
+    const int es_c[2] = {2, 1};
+    const int ws_c[3] = {4, 3, 2};
+    for (int ws : ws_c)
+        for (int es : es_c)
+            for (int xs = kMaxXSlots; xs >= 3; --xs) {
+                if (smem_layout(p.C, xs, ws, es).total <= 227u * 1024u) {
+                    p.xslots = xs;
+                    p.wstages = ws;
+                    p.eslots = es;
+                    return true;
+                }
+            }
+    return false;
 }
 
 inline int launch(Ctx *ctx, int kid, LaunchGcn &L, cudaStream_t st) {
-    const int ws = pick_wstages(L.prm.Cin, L.prm.C);
-    if (!ws) {
+    if (!plan_smem(L.prm)) {
         set_error("gcn_fused: shared memory plan does not fit (Cin=%d C=%d)", L.prm.Cin, L.prm.C);
         return GS_ERR_UNSUPPORTED;
     }
-    L.prm.wstages = ws;
-    const Smem lay = smem_layout(L.prm.Cin, L.prm.C, ws);
+    const Smem lay = smem_layout(L.prm.C, L.prm.xslots, L.prm.wstages, L.prm.eslots);
     int grid = L.prm.ntiles < ctx->sm_count ? L.prm.ntiles : ctx->sm_count;
     if (grid < 1) return GS_OK;
-#define GS_GCN_LAUNCH(S)                                                                                     \
-    do {                                                                                                     \
-        GS_CUDA(cudaFuncSetAttribute(gcn_fused_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                     (int)lay.total));                                                       \
-        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);                                                      \
-        gcn_fused_kernel<S><<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT,  \
-                                                                  L.mapGV, L.prm);                          \
-    } while (0)
-    if (ws == 4) GS_GCN_LAUNCH(4);
-    else if (ws == 3) GS_GCN_LAUNCH(3);
-    else GS_GCN_LAUNCH(2);
-#undef GS_GCN_LAUNCH
+    GS_CUDA(cudaFuncSetAttribute(gcn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    {
+        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
+        gcn_fused_kernel<<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT, L.mapGV,
+                                                               L.prm);
+    }
     GS_KERNEL_CHECK();
     return GS_OK;
 }

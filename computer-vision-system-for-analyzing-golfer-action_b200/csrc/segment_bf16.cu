@@ -32,6 +32,7 @@ struct Bf16Path {
     int maps_T = -1;
     bool fused_gcn = true;      // GOLFER_GCN_UNFUSED=1 selects the SIMT-aggregate + dense-GEMM pair
     bool debug_xa = false;      // GOLFER_DEBUG_XA=1 dumps the fused kernel's XA chunks into bufXA
+    unsigned long long *trace = nullptr;   // GOLFER_TRACE_GCN=1: [blocks][5 roles][6 tiles][64 events] clock64
 };
 
 namespace {
@@ -193,6 +194,13 @@ int bf16_path_create(Ctx *ctx) {
     ctx->bf16 = bp;
     if (const char *e = getenv("GOLFER_GCN_UNFUSED")) bp->fused_gcn = !(e[0] == '1');
     if (const char *e = getenv("GOLFER_DEBUG_XA")) bp->debug_xa = (e[0] == '1');
+    if (const char *e = getenv("GOLFER_TRACE_GCN")) {
+        if (e[0] == '1') {
+            const size_t n = (size_t)GS_MAX_BLOCKS * 5 * gcn::kTraceTiles * gcn::kTraceEv;
+            GS_CUDA(cudaMalloc((void **)&bp->trace, n * 8));
+            GS_CUDA(cudaMemset(bp->trace, 0, n * 8));
+        }
+    }
     const size_t nb = ctx->blocks.size();
     bp->WgT.assign(nb, nullptr);
     bp->W1T.assign(nb, nullptr);
@@ -254,8 +262,26 @@ void bf16_path_destroy(Ctx *ctx) {
             if (p) cudaFree(p);
     for (float *p : bp->bias_t)
         if (p) cudaFree(p);
+    if (bp->trace) cudaFree(bp->trace);
     delete bp;
     ctx->bf16 = nullptr;
+}
+
+int bf16_debug_read(Ctx *ctx, const char *name, void *host, size_t nbytes) {
+    Bf16Path *bp = ctx->bf16;
+    const void *src = nullptr;
+    if (bp && !strcmp(name, "gcn_trace")) src = bp->trace;
+    else if (!strcmp(name, "XA")) src = ctx->bufXA;
+    else if (!strcmp(name, "X")) src = ctx->bufX;
+    else if (!strcmp(name, "Y")) src = ctx->bufY;
+    else if (!strcmp(name, "H")) src = ctx->bufH;
+    if (!src) {
+        set_error("debug buffer '%s' not available", name);
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaDeviceSynchronize());
+    GS_CUDA(cudaMemcpy(host, src, nbytes, cudaMemcpyDeviceToHost));
+    return GS_OK;
 }
 
 int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,
@@ -305,6 +331,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.A = b.A;
             q.bias = b.bg;
             q.dbg_xa = (bp->debug_xa && cin * 128 <= 119 * 256) ? XA : nullptr;
+            q.trace = bp->trace ? bp->trace + (size_t)i * 5 * gcn::kTraceTiles * gcn::kTraceEv : nullptr;
             L.flops = 2.0 * rows * (V17 * 3.0 * cin + 3.0 * cin * C);
             L.bytes = 2.0 * rows * (2.0 * cin + C);
             if ((rc = gcn::launch(ctx, K_B_GEMM_GCN, L, st))) return rc;

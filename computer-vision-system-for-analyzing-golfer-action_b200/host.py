@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
     "gs_compare", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
-    "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read",
+    "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_debug_read",
 )
 
 
@@ -96,6 +96,8 @@ def load_library():
         L.gs_workspace_bytes.restype = ctypes.c_size_t
         L.gs_last_kernel_ms.argtypes = [vp]
         L.gs_last_kernel_ms.restype = ctypes.c_float
+        L.gs_debug_read.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
+        L.gs_debug_read.restype = ctypes.c_int
         L.gs_profile_enable.argtypes = [vp, i32]
         L.gs_profile_reset.argtypes = [vp]
         L.gs_profile_kernels.restype = ctypes.c_int
@@ -175,6 +177,11 @@ class Context:
 
     def last_kernel_ms(self) -> float:
         return float(self._L.gs_last_kernel_ms(self._h))
+
+    def debug_read(self, name: str, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        _check(self._L.gs_debug_read(self._h, name.encode(), out.ctypes.data, nbytes), "gs_debug_read")
+        return out
 
     def profile(self, on: bool):
         _check(self._L.gs_profile_enable(self._h, 1 if on else 0), "gs_profile_enable")

@@ -131,6 +131,10 @@ int gs_compare(gs_ctx *ctx, const float *a_dev, const float *b_dev, const int32_
                const int32_t *path_len_dev, int N, int Ta, int Tb, int V, int Cc,
                float *out_dev, void *cuda_stream);
 
+/* Debug hook: copy a named internal device buffer ("X", "XA", "Y", "H", "gcn_trace") to host
+ * memory after synchronising the device.  Not part of the product surface. */
+int gs_debug_read(gs_ctx *ctx, const char *name, void *host_out, size_t nbytes);
+
 /* Per-kernel profiling for the roofline report: while enabled, every kernel launch is
  * bracketed by a CUDA event pair on its stream.  gs_profile_read synchronises the device,
  * folds the pending event pairs, and returns for kernel index `kernel`
