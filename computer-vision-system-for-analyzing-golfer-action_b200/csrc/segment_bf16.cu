@@ -155,8 +155,6 @@ int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, c
     L.mapB0 = L.mapB1 = w;
     L.mapOut = out;
     L.bias = bias;
-    L.maxBrows = N;
-    L.stages = tc::pick_stages(64, N, N);
     const double rows = (double)B * T * V17;
     L.flops = 2.0 * rows * K * N;
     L.bytes = 2.0 * rows * (K + N);
@@ -384,8 +382,6 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             L.mapB1 = proj ? m.wr : m.w2;
             L.mapOut = m.u_out[i & 1];
             L.bias = bp->bias_t[i];
-            L.maxBrows = proj ? C : cr;
-            L.stages = tc::pick_stages(cr, L.maxBrows, C);
             L.flops = 2.0 * rows * (3.0 * cr * C + (proj ? (double)cin * C : 0.0));
             L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
             if ((rc = tc::launch(ctx, K_B_TCONV, L, st))) return rc;

@@ -22,6 +22,7 @@
 // (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -55,6 +56,13 @@ struct Program {
     int has_residual;   // add residual[b, r, n] (bf16, row stride N) before the activation
     int a_bytes;        // bytes of one A box
     int b_bytes[2];     // bytes of one B box per B map
+    // shared-memory plan (host: plan_smem)
+    int resident;       // 1: every chunk's weight box is loaded ONCE per CTA and stays in smem;
+                        // 0: weight boxes stream through the ring next to the A boxes
+    int stages;         // ring depth
+    int eslots;         // epilogue staging slots (64-column boxes)
+    uint32_t stage_bytes, a_span, w_off, out_off, bar_off, smem_total;
+    uint32_t b_off[kMaxChunks];   // resident mode: byte offset of chunk c's weight box from w_off
     Chunk ch[kMaxChunks];
 };
 
@@ -187,40 +195,23 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-struct SmemPlan {
-    uint32_t stage_bytes, a_bytes, out_off, bar_off, total;
-    int stages;
-};
+constexpr int kMaxStages = 8;
 
-__host__ __device__ inline SmemPlan smem_plan(int kc, int maxBrows, int N, int stages) {
-    SmemPlan p;
-    p.a_bytes = (uint32_t)kTileM * kc * 2;
-    uint32_t bb = (uint32_t)maxBrows * kc * 2;
-    bb = (bb + 1023u) & ~1023u;
-    p.stage_bytes = ((p.a_bytes + 1023u) & ~1023u) + bb;
-    p.stages = stages;
-    p.out_off = p.stage_bytes * stages;
-    p.bar_off = p.out_off + (uint32_t)kTileM * N * 2;
-    p.total = p.bar_off + 256 + 1024;   // barriers + slack for the manual 1024 B alignment
-    return p;
-}
-
-template <int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ Program prog,
-               const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual, int maxBrows) {
+               const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    const SmemPlan plan = smem_plan(prog.kc, maxBrows, prog.N, STAGES);
-    const uint32_t a_span = (plan.a_bytes + 1023u) & ~1023u;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
-    uint64_t *empty = full + STAGES;
-    uint64_t *tfull = empty + STAGES;
+    const int STAGES = prog.stages, ES = prog.eslots;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + prog.bar_off);
+    uint64_t *empty = full + kMaxStages;
+    uint64_t *tfull = empty + kMaxStages;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *wres = tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wres + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -235,7 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapOut);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -243,6 +234,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 1);
         }
+        mbar_init(wres, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
@@ -254,6 +246,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (prog.resident) {
+                // weights: every chunk's box once per CTA (stays resident for all tiles)
+                uint32_t total = 0;
+                for (int c = 0; c < prog.nchunks; ++c) total += (uint32_t)prog.b_bytes[prog.ch[c].b_map];
+                mbar_expect_tx(wres, total);
+                for (int c = 0; c < prog.nchunks; ++c) {
+                    const Chunk &ch = prog.ch[c];
+                    tma_load_2d(smem + prog.w_off + prog.b_off[c], ch.b_map ? &mapB1 : &mapB0, wres, ch.b_k, ch.b_row);
+                }
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
@@ -262,11 +264,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int c = 0; c < prog.nchunks; ++c) {
                     const Chunk &ch = prog.ch[c];
                     mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char *sa = smem + (size_t)stage * plan.stage_bytes;
-                    unsigned char *sb = sa + a_span;
-                    mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes + (uint32_t)prog.b_bytes[ch.b_map]);
+                    unsigned char *sa = smem + (size_t)stage * prog.stage_bytes;
+                    if (prog.resident) {
+                        mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes);
+                    } else {
+                        mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes + (uint32_t)prog.b_bytes[ch.b_map]);
+                        tma_load_2d(sa + prog.a_span, ch.b_map ? &mapB1 : &mapB0, &full[stage], ch.b_k, ch.b_row);
+                    }
                     tma_load_3d(sa, ch.a_map ? &mapA1 : &mapA0, &full[stage], ch.a_k, row0 + ch.a_shift, b);
-                    tma_load_2d(sb, ch.b_map ? &mapB1 : &mapB0, &full[stage], ch.b_k, ch.b_row);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -280,6 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t acc_phase = 0;
             const uint32_t row_bytes = (uint32_t)prog.kc * 2;
             const int ksteps = prog.kc / 16;
+            if (prog.resident) mbar_wait(wres, 0);
             for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -288,9 +294,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const Chunk &ch = prog.ch[c];
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * plan.stage_bytes);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * prog.stage_bytes);
+                    const uint32_t sb = prog.resident ? smem_u32(smem + prog.w_off + prog.b_off[c]) : sa + prog.a_span;
                     const uint64_t da = make_kmajor_desc(sa, row_bytes);
-                    const uint64_t db = make_kmajor_desc(sa + a_span, row_bytes);
+                    const uint64_t db = make_kmajor_desc(sb, row_bytes);
                     const uint32_t idesc = make_idesc_bf16((uint32_t)ch.n_size);
                     for (int k = 0; k < ksteps; ++k) {
                         // +32 bytes of K per step: descriptor start address is in 16 B units
@@ -309,17 +316,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ew = warp - 4;
         const int r = ew * 32 + lane;                  // row inside the tile
         const bool leader = (threadIdx.x == 128);
-        unsigned char *sout = smem + plan.out_off;
+        unsigned char *sout = smem + prog.out_off;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, ecnt = 0;
         for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
             const int b = tile / prog.mtiles;
             const int row0 = (tile % prog.mtiles) * kTileM;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            // staging buffer must no longer be read by the previous tile's TMA store
-            if (leader) tma_store_wait_read0();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             const bool row_ok = (row0 + r) < prog.rows_per_clip;
             const __nv_bfloat16 *res_row =
                 residual + ((size_t)b * prog.rows_per_clip + (size_t)(row0 + r)) * (size_t)N;
@@ -329,7 +333,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                 tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                 tmem_ld_wait();
-                unsigned char *box = sout + (size_t)q * (kTileM * 128);
+                if (q == N / 64 - 1) {
+                    // every TMEM read of this accumulator is done: hand it back to the MMA warp
+                    tc_fence_before();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (leader) mbar_arrive(&tempty[acc]);
+                }
+                // staging slot reuse: the TMA store issued ES boxes ago must have finished reading it
+                const uint32_t es = ecnt % (uint32_t)ES;
+                if (leader && ecnt >= (uint32_t)ES) {
+                    if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                unsigned char *box = sout + (size_t)es * (kTileM * 128);
 #pragma unroll
                 for (int cchunk = 0; cchunk < 8; ++cchunk) {
                     float f[8];
@@ -357,16 +374,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     // 128B-swizzled box row: 16 B chunk index XOR (row & 7) — matches the TMA map
                     *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cchunk ^ (r & 7)) << 4)) = packed;
                 }
-            }
-            // TMEM reads of this accumulator are done (wait::ld above): hand it back to the MMA warp
-            tc_fence_before();
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (leader) {
-                mbar_arrive(&tempty[acc]);
-                for (int q = 0; q < N / 64; ++q)
-                    tma_store_3d(&mapOut, sout + (size_t)q * (kTileM * 128), q * 64, row0, b);
-                tma_store_commit();
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    tma_store_3d(&mapOut, box, q * 64, row0, b);
+                    tma_store_commit();
+                }
+                ++ecnt;
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -474,40 +488,78 @@ struct Launch {
     Program prog;
     const float *bias = nullptr;
     const __nv_bfloat16 *residual = nullptr;
-    int maxBrows = 0;
-    int stages = 4;
     double flops = 0, bytes = 0;   // algorithmic, for the profiler
 };
 
-inline int pick_stages(int kc, int maxBrows, int N) {
-    const int cand[4] = {6, 4, 3, 2};
-    for (int s : cand)
-        if (smem_plan(kc, maxBrows, N, s).total <= 227u * 1024u) return s;
-    return 0;
+// Fill the shared-memory plan of `p` (nchunks, kc, N, a_bytes, b_bytes, ch[] must be set).
+// Weights stay resident when they fit next to >= 3 A stages; otherwise they stream with A.
+inline bool plan_smem(Program &p, bool allow_resident = true) {
+    const uint32_t limit = 227u * 1024u;
+    const uint32_t a_span = ((uint32_t)p.a_bytes + 1023u) & ~1023u;
+    const uint32_t bars = 512, slack = 1024;
+    uint32_t wtotal = 0;
+    for (int c = 0; c < p.nchunks; ++c) {
+        p.b_off[c] = wtotal;
+        wtotal += ((uint32_t)p.b_bytes[p.ch[c].b_map] + 1023u) & ~1023u;
+    }
+    const int es_c[2] = {2, 1};
+    if (allow_resident) {
+        for (int es : es_c)
+            for (int st = kMaxStages; st >= 3; --st) {
+                const uint32_t tot = wtotal + a_span * st + (uint32_t)es * 16384u + bars + slack;
+                if (tot <= limit) {
+                    p.resident = 1;
+                    p.stages = st;
+                    p.eslots = es;
+                    p.a_span = a_span;
+                    p.stage_bytes = a_span;
+                    p.w_off = a_span * st;
+                    p.out_off = p.w_off + wtotal;
+                    p.bar_off = p.out_off + (uint32_t)es * 16384u;
+                    p.smem_total = p.bar_off + bars + slack;
+                    return true;
+                }
+            }
+    }
+    uint32_t bmax = 0;
+    for (int c = 0; c < p.nchunks; ++c) {
+        const uint32_t b = ((uint32_t)p.b_bytes[p.ch[c].b_map] + 1023u) & ~1023u;
+        bmax = b > bmax ? b : bmax;
+    }
+    for (int es : es_c)
+        for (int st = kMaxStages; st >= 2; --st) {
+            const uint32_t tot = (a_span + bmax) * st + (uint32_t)es * 16384u + bars + slack;
+            if (tot <= limit) {
+                p.resident = 0;
+                p.stages = st;
+                p.eslots = es;
+                p.a_span = a_span;
+                p.stage_bytes = a_span + bmax;
+                p.w_off = 0;
+                p.out_off = p.stage_bytes * st;
+                p.bar_off = p.out_off + (uint32_t)es * 16384u;
+                p.smem_total = p.bar_off + bars + slack;
+                return true;
+            }
+        }
+    return false;
 }
 
-inline int launch(Ctx *ctx, int kid, const Launch &L, cudaStream_t st) {
-    const SmemPlan plan = smem_plan(L.prog.kc, L.maxBrows, L.prog.N, L.stages);
+inline int launch(Ctx *ctx, int kid, Launch &L, cudaStream_t st) {
+    static const bool no_resident = getenv("GOLFER_TC_STREAM_WEIGHTS") != nullptr;
+    if (!plan_smem(L.prog, !no_resident)) {
+        set_error("tc_gemm: shared memory plan does not fit (kc=%d N=%d chunks=%d)", L.prog.kc, L.prog.N,
+                  L.prog.nchunks);
+        return GS_ERR_UNSUPPORTED;
+    }
     int grid = L.prog.ntiles < ctx->sm_count ? L.prog.ntiles : ctx->sm_count;
     if (grid < 1) return GS_OK;
-#define GS_TC_LAUNCH(S)                                                                                        \
-    do {                                                                                                       \
-        GS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                     (int)plan.total));                                                        \
-        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);                                                        \
-        tc_gemm_kernel<S><<<grid, kThreads, plan.total, st>>>(L.mapA0, L.mapA1, L.mapB0, L.mapB1, L.mapOut,    \
-                                                              L.prog, L.bias, L.residual, L.maxBrows);         \
-    } while (0)
-    switch (L.stages) {
-        case 2: GS_TC_LAUNCH(2); break;
-        case 3: GS_TC_LAUNCH(3); break;
-        case 4: GS_TC_LAUNCH(4); break;
-        case 6: GS_TC_LAUNCH(6); break;
-        default:
-            set_error("tc_gemm: unsupported stage count %d", L.stages);
-            return GS_ERR_UNSUPPORTED;
+    GS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.prog.smem_total));
+    {
+        LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
+        tc_gemm_kernel<<<grid, kThreads, L.prog.smem_total, st>>>(L.mapA0, L.mapA1, L.mapB0, L.mapB1, L.mapOut, L.prog,
+                                                                  L.bias, L.residual);
     }
-#undef GS_TC_LAUNCH
     GS_KERNEL_CHECK();
     return GS_OK;
 }
