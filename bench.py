@@ -293,7 +293,9 @@ def main():
             kernels[name] = {"share": round(v["ms"] / tot, 4), "ms_per_launch": v["ms"] / v["launches"],
                              "launches_per_step": v["launches"] / K,
                              "tflops": v["flops"] / v["ms"] / 1e9 if v["ms"] else 0.0,
-                             "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] else 0.0}
+                             "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] else 0.0,
+                             "ms_per_launch_by_block": {str(bk): round(bv["ms"] / bv["launches"], 4)
+                                                        for bk, bv in v.get("blocks", {}).items()}}
         top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
         tensor_bound = "gemm" in top or "tconv" in top
         if tensor_bound:

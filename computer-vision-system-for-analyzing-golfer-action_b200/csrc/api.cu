@@ -53,8 +53,12 @@ int validate_cfg(const gs_config *c) {
     }
     for (int i = 0; i < c->num_blocks; ++i) {
         const int w = c->widths[i];
-        if (w < 1 || w > 1024 || w % c->num_branches || w % c->se_reduction || w % c->stj_reduction) {
-            set_error("width[%d]=%d invalid (<=1024, divisible by branches and reductions)", i, w);
+        if (w < 8 || w > 1024 || w % 8 || w % c->num_branches || w % c->se_reduction || w % c->stj_reduction) {
+            set_error("width[%d]=%d invalid (8..1024, multiple of 8, divisible by branches and reductions)", i, w);
+            return GS_ERR_INVALID;
+        }
+        if ((w / c->stj_reduction) % 2) {
+            set_error("width[%d]/stj_reduction must be even", i);
             return GS_ERR_INVALID;
         }
     }
@@ -70,14 +74,20 @@ int validate_cfg(const gs_config *c) {
     return GS_OK;
 }
 
-// Walk the folded blob in params.py:fold_params order.
+// Walk the folded blob in params.py:fold_params order.  Every tensor is re-based to a
+// 16-byte aligned offset in the device copy (kernels read weights with vector loads);
+// ctx->h_blob mirrors the device layout.
 int parse_blob(Ctx *ctx, const float *host, size_t nfloats) {
     const gs_config &c = ctx->cfg;
     const int V = c.num_joints, P = c.num_partitions, R = c.num_branches;
-    size_t off = 0;
+    size_t off = 0, doff = 0;
+    std::vector<float> &staged = ctx->h_blob;
     auto take = [&](size_t n) {
-        const float *p = ctx->d_blob + off;
+        const float *p = ctx->d_blob + doff;
+        if (off + n <= nfloats && doff + n <= staged.size())
+            memcpy(staged.data() + doff, host + off, n * sizeof(float));
         off += n;
+        doff = (doff + n + 3) & ~(size_t)3;
         return p;
     };
     ctx->in_scale = take((size_t)V * c.in_channels);
@@ -118,11 +128,14 @@ int parse_blob(Ctx *ctx, const float *host, size_t nfloats) {
     }
     ctx->headW = take((size_t)cin * c.num_classes);
     ctx->headb = take(c.num_classes);
-    if (off != nfloats) {
+    if (off != nfloats || doff > staged.size()) {
         set_error("weight blob holds %zu floats, config needs %zu", nfloats, off);
         return GS_ERR_INVALID;
     }
-    (void)host;
+    if (cudaMemcpy(ctx->d_blob, staged.data(), doff * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("weight upload failed");
+        return GS_ERR_CUDA;
+    }
     return GS_OK;
 }
 
@@ -159,7 +172,7 @@ void free_ctx(Ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->bf16) bf16_path_destroy(ctx);
-    void *ptrs[] = {ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
+    void *ptrs[] = {ctx->headWT, ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
                     ctx->bufU[1], ctx->PT, ctx->PV, ctx->PVpart, ctx->seS, ctx->gT, ctx->gV, ctx->d_skel,
                     ctx->d_logits, ctx->d_labels, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
                     ctx->d_al_path, ctx->d_al_plen};
@@ -284,17 +297,26 @@ int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weight
             rc = GS_ERR_INVALID;
             break;
         }
-        if ((rc = dmalloc(ctx, &ctx->d_blob, nfloats))) break;
+        const size_t padded = nfloats + 4 * (size_t)(32 * cfg->num_blocks + 16);   // room for per-tensor alignment
+        if ((rc = dmalloc(ctx, &ctx->d_blob, padded))) break;
         ctx->blob_floats = nfloats;
         const float *body = (const float *)weights_blob + 4;
-        if (cudaMemcpy(ctx->d_blob, body, nfloats * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("weight upload failed");
-            rc = GS_ERR_CUDA;
-            break;
-        }
-        ctx->h_blob.assign(body, body + nfloats);
+        ctx->h_blob.assign(padded, 0.f);
         if ((rc = parse_blob(ctx, body, nfloats))) break;
         if ((rc = alloc_workspace(ctx))) break;
+        {   // head weights [C,K] -> [K,C]
+            const int C = cfg->widths[cfg->num_blocks - 1], K = cfg->num_classes;
+            const float *hw = ctx->h_blob.data() + (ctx->headW - ctx->d_blob);
+            std::vector<float> t((size_t)K * C);
+            for (int c = 0; c < C; ++c)
+                for (int k = 0; k < K; ++k) t[(size_t)k * C + c] = hw[(size_t)c * K + k];
+            if ((rc = dmalloc(ctx, &ctx->headWT, t.size()))) break;
+            if (cudaMemcpy(ctx->headWT, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("head weight upload failed");
+                rc = GS_ERR_CUDA;
+                break;
+            }
+        }
         ctx->has_net = true;
         if (cfg->precision == GS_PREC_BF16 && (rc = bf16_path_create(ctx))) break;
     } while (0);
@@ -515,26 +537,49 @@ int gs_profile_reset(gs_ctx *h) {
     if (!ctx) return GS_ERR_INVALID;
     Profiler &p = ctx->prof;
     p.used = 0;
-    for (int i = 0; i < K_COUNT; ++i) p.ms[i] = p.flops[i] = p.bytes[i] = 0, p.launches[i] = 0;
+    for (int i = 0; i < K_COUNT; ++i) {
+        p.ms[i] = p.flops[i] = p.bytes[i] = 0, p.launches[i] = 0;
+        for (int b = 0; b <= GS_MAX_BLOCKS; ++b) p.ms_blk[i][b] = 0, p.launches_blk[i][b] = 0;
+    }
     return GS_OK;
 }
 
 int gs_profile_kernels(void) { return K_COUNT; }
 
-int gs_profile_read(gs_ctx *h, int kernel, const char **name, double *total_ms, int64_t *launches,
-                    double *alg_flops, double *alg_bytes) {
-    Ctx *ctx = (Ctx *)h;
-    if (!ctx || kernel < 0 || kernel >= K_COUNT) return GS_ERR_INVALID;
+static int profile_fold(Ctx *ctx) {
     Profiler &p = ctx->prof;
     if (p.used) {   // fold the recorded event pairs into the per-kernel totals
         GS_CUDA(cudaSetDevice(ctx->device));
         GS_CUDA(cudaDeviceSynchronize());
         for (size_t i = 0; i < p.used; ++i) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, p.pool[i].e0, p.pool[i].e1) == cudaSuccess) p.ms[p.pool[i].id] += ms;
+            if (cudaEventElapsedTime(&ms, p.pool[i].e0, p.pool[i].e1) == cudaSuccess) {
+                p.ms[p.pool[i].id] += ms;
+                p.ms_blk[p.pool[i].id][p.pool[i].blk] += ms;
+            }
         }
         p.used = 0;
     }
+    return GS_OK;
+}
+
+int gs_profile_read_block(gs_ctx *h, int kernel, int block, double *total_ms, int64_t *launches) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || kernel < 0 || kernel >= K_COUNT || block < 0 || block > GS_MAX_BLOCKS) return GS_ERR_INVALID;
+    int rc = profile_fold(ctx);
+    if (rc) return rc;
+    if (total_ms) *total_ms = ctx->prof.ms_blk[kernel][block];
+    if (launches) *launches = ctx->prof.launches_blk[kernel][block];
+    return GS_OK;
+}
+
+int gs_profile_read(gs_ctx *h, int kernel, const char **name, double *total_ms, int64_t *launches,
+                    double *alg_flops, double *alg_bytes) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || kernel < 0 || kernel >= K_COUNT) return GS_ERR_INVALID;
+    Profiler &p = ctx->prof;
+    int rc = profile_fold(ctx);
+    if (rc) return rc;
     if (name) *name = kernel_name(kernel);
     if (total_ms) *total_ms = p.ms[kernel];
     if (launches) *launches = p.launches[kernel];

@@ -63,7 +63,7 @@ const char *kernel_name(int id);
 
 struct ProfSlot {
     cudaEvent_t e0, e1;
-    int id;
+    int id, blk;
 };
 
 struct Profiler {
@@ -74,6 +74,9 @@ struct Profiler {
     double flops[K_COUNT] = {0};
     double bytes[K_COUNT] = {0};
     int64_t launches[K_COUNT] = {0};
+    // the same, split by network block (index GS_MAX_BLOCKS = launches outside any block)
+    double ms_blk[K_COUNT][GS_MAX_BLOCKS + 1] = {{0}};
+    int64_t launches_blk[K_COUNT][GS_MAX_BLOCKS + 1] = {{0}};
 };
 
 struct Ctx {
@@ -84,12 +87,14 @@ struct Ctx {
     int max_B = 0, max_T = 0;
     int64_t launches = 0;
     size_t ws_bytes = 0;
+    int cur_block = GS_MAX_BLOCKS;   // network block the forward pass is in (profiler attribution)
 
     // weights
     float *d_blob = nullptr;      // whole folded blob (fp32)
     std::vector<float> h_blob;    // host copy (bf16 path repacks weights from it)
     size_t blob_floats = 0;
     const float *in_scale = nullptr, *in_shift = nullptr, *headW = nullptr, *headb = nullptr;
+    float *headWT = nullptr;      // head weights transposed to [K][C] (head_kernel stages rows)
     std::vector<BlockParams> blocks;
 
     // segmentation workspace (element type depends on precision)
@@ -135,6 +140,7 @@ struct LaunchScope {
         Profiler &p = c->prof;
         if (!p.on) return;
         p.launches[id] += 1;
+        p.launches_blk[id][c->cur_block] += 1;
         p.flops[id] += flops;
         p.bytes[id] += bytes;
         if (p.used == p.pool.size()) {
@@ -145,6 +151,7 @@ struct LaunchScope {
         }
         slot = (int)p.used++;
         p.pool[slot].id = id;
+        p.pool[slot].blk = c->cur_block;
         cudaEventRecord(p.pool[slot].e0, st);
     }
     ~LaunchScope() {

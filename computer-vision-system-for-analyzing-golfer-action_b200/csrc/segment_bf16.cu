@@ -38,48 +38,112 @@ struct Bf16Path {
 namespace {
 
 // ---- block 0 on CUDA cores: input BN + adjacency + K=9 mix (+ReLU) and K=3 residual ------
-constexpr int kFrontFrames = 8;
+// One CTA = kFrontFrames frames.  Phase 3 work unit = (row, 4 output channels): the row's 3*Cin
+// aggregated inputs and Cin raw inputs against the thread's weight columns held in registers,
+// packed to two 8-byte bf16 stores (Y and the residual projection R0); a warp writes 256
+// contiguous bytes of each.  C/4 must divide 256.
+constexpr int kFrontFrames = 16;
 
+struct FrontSmem {
+    int a, w, bias, x, xa, total;   // float offsets
+};
+__host__ __device__ inline FrontSmem front_smem(int Cin, int C) {
+    FrontSmem s;
+    s.a = 0;
+    s.w = s.a + 3 * V17 * V17 + 1;
+    s.bias = s.w;
+    s.x = s.bias;
+    s.xa = s.x + kFrontFrames * V17 * Cin;
+    s.total = s.xa + kFrontFrames * V17 * 3 * Cin;
+    return s;
+}
+
+template <int CIN>
 __global__ void __launch_bounds__(256)
 front_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale, const float *__restrict__ in_shift,
              const float *__restrict__ A, const float *__restrict__ Wg, const float *__restrict__ bg,
-             const float *__restrict__ Wr, const float *__restrict__ br, int Cin, int C, size_t nframes,
+             const float *__restrict__ Wr, const float *__restrict__ br, int C, size_t nframes,
              __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ R0) {
-    extern __shared__ float sm[];
-    const int K3 = 3 * Cin;
-    float *sA = sm;                                   // [3*17*17]
-    float *sx = sA + 3 * V17 * V17;                   // [FR*17*Cin]
-    float *sxa = sx + kFrontFrames * V17 * Cin;       // [FR*17*3Cin]
+    extern __shared__ __align__(16) float sm[];
+    constexpr int K3 = 3 * CIN;
+    const FrontSmem lay = front_smem(CIN, C);
+    float *sA = sm + lay.a, *sx = sm + lay.x, *sxa = sm + lay.xa;
     for (int k = threadIdx.x; k < 3 * V17 * V17; k += blockDim.x) sA[k] = A[k];
     const size_t f0 = (size_t)blockIdx.x * kFrontFrames;
     const int nf = (int)(nframes - f0 < (size_t)kFrontFrames ? nframes - f0 : (size_t)kFrontFrames);
-    for (int e = threadIdx.x; e < nf * V17 * Cin; e += blockDim.x) {
-        const int vc = e % (V17 * Cin);
-        sx[e] = skel[f0 * V17 * Cin + e] * in_scale[vc] + in_shift[vc];
+    for (int e = threadIdx.x; e < nf * V17 * CIN; e += blockDim.x) {
+        const int vc = e % (V17 * CIN);
+        sx[e] = skel[f0 * V17 * CIN + e] * in_scale[vc] + in_shift[vc];
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nf * V17 * K3; e += blockDim.x) {
-        const int k = e % K3, w = (e / K3) % V17, f = e / (K3 * V17);
-        const int p = k / Cin, c = k % Cin;
-        const float *ar = sA + (p * V17 + w) * V17;
-        const float *xf = sx + f * V17 * Cin + c;
-        float acc = 0.f;
+    // this thread's 4 output channels never change (C/4 divides the block size): weights in registers
+    const int ng = C / 4;
+    const int c0 = (threadIdx.x % ng) * 4;
+    float wreg[K3 + CIN][4], breg[2][4];
 #pragma unroll
-        for (int v = 0; v < V17; ++v) acc += ar[v] * xf[v * Cin];
-        sxa[e] = acc;
+    for (int k = 0; k < K3 + CIN; ++k) {
+        const float *src = k < K3 ? Wg + (size_t)k * C + c0 : Wr + (size_t)(k - K3) * C + c0;
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src));
+        wreg[k][0] = w0.x; wreg[k][1] = w0.y; wreg[k][2] = w0.z; wreg[k][3] = w0.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        breg[0][e] = bg[c0 + e];
+        breg[1][e] = br[c0 + e];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < nf * V17 * C; e += blockDim.x) {
-        const int co = e % C, row = e / C;
-        const float *xa = sxa + row * K3;
-        float y = bg[co];
-        for (int k = 0; k < K3; ++k) y += xa[k] * Wg[k * C + co];
-        const float *x = sx + row * Cin;
-        float r = br[co];
-        for (int c = 0; c < Cin; ++c) r += x[c] * Wr[c * C + co];
-        const size_t o = (f0 * V17 + row) * C + co;
-        Y[o] = __float2bfloat16_rn(fmaxf(y, 0.f));
-        R0[o] = __float2bfloat16_rn(r);
+    // adjacency contraction: unit = (frame, output joint w) -> the 3*CIN aggregated inputs of that row
+    for (int u = threadIdx.x; u < nf * V17; u += blockDim.x) {
+        const int f = u / V17, w = u - f * V17;
+        float acc[K3];
+#pragma unroll
+        for (int k = 0; k < K3; ++k) acc[k] = 0.f;
+        const float *xf = sx + f * V17 * CIN;
+#pragma unroll
+        for (int v = 0; v < V17; ++v) {
+            float x[CIN];
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) x[c] = xf[v * CIN + c];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const float a = sA[(p * V17 + w) * V17 + v];
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) acc[p * CIN + c] += a * x[c];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K3; ++k) sxa[u * K3 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < nf * V17 * ng; u += blockDim.x) {
+        const int row = u / ng;
+        float y[4], r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            y[e] = breg[0][e];
+            r[e] = breg[1][e];
+        }
+#pragma unroll
+        for (int k = 0; k < K3; ++k) {
+            const float a = sxa[row * K3 + k];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] += a * wreg[k][e];
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float a = sx[row * CIN + c];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] += a * wreg[K3 + c][e];
+        }
+        uint2 py, pr;
+        __nv_bfloat162 *hy = reinterpret_cast<__nv_bfloat162 *>(&py), *hr = reinterpret_cast<__nv_bfloat162 *>(&pr);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            hy[e] = __floats2bfloat162_rn(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
+            hr[e] = __floats2bfloat162_rn(r[2 * e], r[2 * e + 1]);
+        }
+        const size_t o = (f0 * V17 + row) * C + c0;
+        *reinterpret_cast<uint2 *>(Y + o) = py;
+        *reinterpret_cast<uint2 *>(R0 + o) = pr;
     }
 }
 
@@ -166,8 +230,9 @@ int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, c
 int bf16_path_create(Ctx *ctx) {
     const gs_config &c = ctx->cfg;
     const int R = c.num_branches;
-    if (ctx->blocks.empty() || !ctx->blocks[0].has_res) {
-        set_error("bf16 path expects block 0 to change width (residual projection)");
+    if (ctx->blocks.empty() || !ctx->blocks[0].has_res || c.in_channels != 3 ||
+        256 % (ctx->blocks[0].c / 4) != 0) {
+        set_error("bf16 path expects 3 input channels and block 0 to change width (residual projection)");
         return GS_ERR_UNSUPPORTED;
     }
     for (size_t i = 0; i < ctx->blocks.size(); ++i) {
@@ -295,17 +360,20 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
     bf *X = (bf *)ctx->bufX, *XA = (bf *)ctx->bufXA, *Y = (bf *)ctx->bufY, *R0 = (bf *)ctx->bufR;
     const bf *Uprev = nullptr;
     for (int i = 0; i <= last; ++i) {
+        ctx->cur_block = i;
         const BlockParams &b = ctx->blocks[i];
         const BlockMaps &m = bp->maps[i];
         const int C = b.c, cin = b.cin, cr = b.cr;
         bf *U = (bf *)ctx->bufU[i & 1];
         if (i == 0) {
-            const size_t smem = (3 * V17 * V17 + kFrontFrames * V17 * cin * 4) * sizeof(float);
+            const size_t smem = (size_t)front_smem(cin, C).total * sizeof(float);
+            if (smem > 48 * 1024)
+                GS_CUDA(cudaFuncSetAttribute(front_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
                                rows * (cin * 4 + 4.0 * C));
-                front_kernel<<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
-                    skel, ctx->in_scale, ctx->in_shift, b.A, b.Wg, b.bg, b.Wr, b.br, cin, C, nframes, Y, R0);
+                front_kernel<3><<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
+                    skel, ctx->in_scale, ctx->in_shift, b.A, b.Wg, b.bg, b.Wr, b.br, C, nframes, Y, R0);
             }
             GS_KERNEL_CHECK();
         } else if (bp->fused_gcn) {
@@ -389,6 +457,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         if ((rc = launch_attention<bf>(ctx, b, U, B, T, st))) return rc;
         Uprev = U;
     }
+    ctx->cur_block = GS_MAX_BLOCKS;
     const int C = ctx->blocks[last].c;
     if (feat_out) return launch_features<bf>(ctx, Uprev, B, T, C, feat_out, st);
     return launch_head<bf>(ctx, Uprev, B, T, C, logits, labels, st);

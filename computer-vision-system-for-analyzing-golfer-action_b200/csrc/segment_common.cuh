@@ -11,6 +11,8 @@
 //   gV[b,v,c] = a_v[b,v,c]
 // are applied by whichever kernel reads U next (next block's aggregation, head).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gs {
@@ -111,124 +113,256 @@ stats_kernel(const TU *__restrict__ U, int T, int C, float *__restrict__ PT, flo
     for (int v = 0; v < V; ++v) PVpart[(((size_t)b * nchunk + chunk) * V + v) * C + c] = pv[v];
 }
 
-// grid B, block = C threads (C <= 1024).  smem: C + cs floats.
+// ---- SE channel attention (README.md:31-32) ---------------------------------------
+// grid B, block 1024 = G groups x C channels (G = min(1024/C, V)).  Group g folds the
+// per-chunk partial sums of joints v = g, g+G, ... into PV[b,v,c]; the clip mean over (T,V)
+// is the fixed-order sum of those; then FC -> ReLU -> FC -> sigmoid with K split over groups.
+// smem floats: G*C (partials) + C (mean) + cs (hidden).
 template <int V>
 __global__ void __launch_bounds__(1024)
-se_kernel(const float *__restrict__ PT, const float *__restrict__ PVpart, int T, int C, int cs, int nchunk,
+se_kernel(const float *__restrict__ PVpart, int T, int C, int cs, int nchunk, int G,
           const float *__restrict__ W1, const float *__restrict__ b1, const float *__restrict__ W2,
           const float *__restrict__ b2, float *__restrict__ seS, float *__restrict__ PV) {
     extern __shared__ float sm[];
-    float *m = sm, *hid = sm + C;
-    const int b = blockIdx.x, c = threadIdx.x;
-    if (c < C) {
+    float *part = sm, *m = sm + G * C, *hid = m + C;
+    const int b = blockIdx.x;
+    const int c = threadIdx.x % C, g = threadIdx.x / C;
+    if (g < G) {
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += PT[((size_t)b * T + t) * C + c];
-        m[c] = acc / (float)(T * V);
-        for (int v = 0; v < V; ++v) {
+        for (int v = g; v < V; v += G) {
             float s = 0.f;
             for (int k = 0; k < nchunk; ++k) s += PVpart[(((size_t)b * nchunk + k) * V + v) * C + c];
             PV[((size_t)b * V + v) * C + c] = s;
+            acc += s;
+        }
+        part[g * C + c] = acc;
+    }
+    __syncthreads();
+    if (g == 0) {
+        float acc = 0.f;
+        for (int k = 0; k < G; ++k) acc += part[k * C + c];
+        m[c] = acc / (float)(T * V);
+    }
+    __syncthreads();
+    // FC1: hid[j] = relu(b1[j] + sum_k m[k] W1[k,j]); K split over P1 parts, fixed-order fold
+    const int P1 = max(1, min((int)blockDim.x / cs, 32));
+    {
+        const int j = threadIdx.x % cs, pt = threadIdx.x / cs;
+        if (pt < P1) {
+            float acc = 0.f;
+            for (int k = pt; k < C; k += P1) acc += m[k] * W1[k * cs + j];
+            part[pt * cs + j] = acc;
         }
     }
     __syncthreads();
-    if (c < cs) {
-        float acc = b1[c];
-        for (int k = 0; k < C; ++k) acc += m[k] * W1[k * cs + c];
-        hid[c] = fmaxf(acc, 0.f);
+    if (threadIdx.x < cs) {
+        float acc = b1[threadIdx.x];
+        for (int p = 0; p < P1; ++p) acc += part[p * cs + threadIdx.x];
+        hid[threadIdx.x] = fmaxf(acc, 0.f);
     }
     __syncthreads();
-    if (c < C) {
+    if (g == 0) {
         float acc = b2[c];
         for (int k = 0; k < cs; ++k) acc += hid[k] * W2[k * C + c];
         seS[(size_t)b * C + c] = sigmoidf_acc(acc);
     }
 }
 
-constexpr int kStjPos = 8;   // positions (frames or joints) per CTA
+// ---- ST-joint attention (README.md:33-34) --------------------------------------------
+// Position tiles of kStjPos: blockIdx.x < ntT covers frames, the rest joints, so one CTA
+// uses one output matrix (Wt or Wv).  Register-tiled SIMT GEMMs: a work unit is one output
+// column x 8 positions (two broadcast LDS.128 + one coalesced weight load per 8 FMAs).
+// smem floats: C*(kStjPos+4) pooled (transposed, padded) + cj*kStjPos hidden.
+constexpr int kStjPos = 32;
+constexpr int kStjLd = kStjPos + 4;
 
-// grid (ceil((T+V)/kStjPos), B), block = C threads.  smem: kStjPos*(C+cj) floats.
 template <int V>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 stj_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const float *__restrict__ seS, int T,
-           int C, int cj, const float *__restrict__ W, const float *__restrict__ bW,
+           int C, int cj, int ntT, const float *__restrict__ W, const float *__restrict__ bW,
            const float *__restrict__ Wt, const float *__restrict__ bt, const float *__restrict__ Wv,
            const float *__restrict__ bv, float *__restrict__ gT, float *__restrict__ gV) {
-    extern __shared__ float sm[];
-    float *pooled = sm;                 // [kStjPos][C]
-    float *att = sm + kStjPos * C;      // [kStjPos][cj]
-    const int b = blockIdx.y, c = threadIdx.x;
-    const int p0 = blockIdx.x * kStjPos;
-    const int np = min(kStjPos, T + V - p0);
-    const float s = c < C ? seS[(size_t)b * C + c] : 0.f;
-    if (c < C) {
-        for (int q = 0; q < np; ++q) {
-            const int pos = p0 + q;
-            float x;
-            if (pos < T) x = PT[((size_t)b * T + pos) * C + c] / (float)V;
-            else x = PV[((size_t)b * V + (pos - T)) * C + c] / (float)T;
-            pooled[q * C + c] = s * x;
+    extern __shared__ __align__(16) float sm[];
+    float *pooled = sm;                    // [C][kStjLd]   pooled[c][q]
+    float *att = sm + (size_t)C * kStjLd;  // [cj][kStjPos] att[k][q]
+    const int b = blockIdx.y;
+    const bool is_t = (int)blockIdx.x < ntT;
+    const int p0 = (is_t ? blockIdx.x : blockIdx.x - ntT) * kStjPos;
+    const int np = min(kStjPos, (is_t ? T : V) - p0);
+    const float inv = is_t ? 1.0f / (float)V : 1.0f / (float)T;
+    const float *src = is_t ? PT + ((size_t)b * T + p0) * C : PV + ((size_t)b * V + p0) * C;
+    for (int e = threadIdx.x; e < kStjPos * C; e += blockDim.x) {
+        const int q = e / C, c = e - q * C;
+        // oracle order: (sum / count) scaled by the SE gate
+        pooled[c * kStjLd + q] = q < np ? seS[(size_t)b * C + c] * (src[(size_t)q * C + c] * inv) : 0.f;
+    }
+    __syncthreads();
+    // phase 1: att[k][q] = hswish(bW[k] + sum_i pooled[i][q] W[i][k]); unit = 2 k x 8 positions
+    for (int u = threadIdx.x; u < (cj / 2) * (kStjPos / 8); u += blockDim.x) {
+        const int k = (u % (cj / 2)) * 2, q8 = (u / (cj / 2)) * 8;
+        float acc[2][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+        const float *pp = pooled + q8;
+#pragma unroll 4
+        for (int i = 0; i < C; ++i) {
+            const float2 w = __ldg(reinterpret_cast<const float2 *>(W + (size_t)i * cj + k));
+            const float4 a = *reinterpret_cast<const float4 *>(pp + i * kStjLd);
+            const float4 d = *reinterpret_cast<const float4 *>(pp + i * kStjLd + 4);
+            const float p[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                acc[0][e] += p[e] * w.x;
+                acc[1][e] += p[e] * w.y;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const float bk = bW[k + kk];
+            float4 o0, o1;
+            o0.x = hardswishf(acc[kk][0] + bk); o0.y = hardswishf(acc[kk][1] + bk);
+            o0.z = hardswishf(acc[kk][2] + bk); o0.w = hardswishf(acc[kk][3] + bk);
+            o1.x = hardswishf(acc[kk][4] + bk); o1.y = hardswishf(acc[kk][5] + bk);
+            o1.z = hardswishf(acc[kk][6] + bk); o1.w = hardswishf(acc[kk][7] + bk);
+            *reinterpret_cast<float4 *>(att + (k + kk) * kStjPos + q8) = o0;
+            *reinterpret_cast<float4 *>(att + (k + kk) * kStjPos + q8 + 4) = o1;
         }
     }
     __syncthreads();
-    for (int e = c; e < np * cj; e += blockDim.x) {
-        const int q = e / cj, k = e % cj;
-        float acc = bW[k];
-        for (int i = 0; i < C; ++i) acc += pooled[q * C + i] * W[i * cj + k];
-        att[q * cj + k] = hardswishf(acc);
-    }
-    __syncthreads();
-    if (c < C) {
-        for (int q = 0; q < np; ++q) {
-            const int pos = p0 + q;
-            const bool is_t = pos < T;
-            const float *Wo = is_t ? Wt : Wv;
-            float acc = is_t ? bt[c] : bv[c];
-            for (int k = 0; k < cj; ++k) acc += att[q * cj + k] * Wo[k * C + c];
-            const float g = sigmoidf_acc(acc);
-            if (is_t) gT[((size_t)b * T + pos) * C + c] = s * g;
-            else gV[((size_t)b * V + (pos - T)) * C + c] = g;
+    // phase 2: gate[q][c] = sigmoid(bo[c] + sum_k att[k][q] Wo[k][c]); unit = 4 channels x 8 positions
+    const float *Wo = is_t ? Wt : Wv;
+    const float *bo = is_t ? bt : bv;
+    float *dst = is_t ? gT + ((size_t)b * T + p0) * C : gV + ((size_t)b * V + p0) * C;
+    for (int u = threadIdx.x; u < (C / 4) * (kStjPos / 8); u += blockDim.x) {
+        const int c = (u % (C / 4)) * 4, q8 = (u / (C / 4)) * 8;
+        if (q8 >= np) continue;
+        float acc[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+        const float *ap = att + q8;
+#pragma unroll 2
+        for (int k = 0; k < cj; ++k) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(Wo + (size_t)k * C + c));
+            const float4 a = *reinterpret_cast<const float4 *>(ap + k * kStjPos);
+            const float4 d = *reinterpret_cast<const float4 *>(ap + k * kStjPos + 4);
+            const float p[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                acc[0][e] += p[e] * w.x;
+                acc[1][e] += p[e] * w.y;
+                acc[2][e] += p[e] * w.z;
+                acc[3][e] += p[e] * w.w;
+            }
+        }
+        const float4 bc = __ldg(reinterpret_cast<const float4 *>(bo + c));
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (is_t) s4 = __ldg(reinterpret_cast<const float4 *>(seS + (size_t)b * C + c));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (q8 + e >= np) break;
+            float4 o;
+            o.x = s4.x * sigmoidf_acc(acc[0][e] + bc.x);
+            o.y = s4.y * sigmoidf_acc(acc[1][e] + bc.y);
+            o.z = s4.z * sigmoidf_acc(acc[2][e] + bc.z);
+            o.w = s4.w * sigmoidf_acc(acc[3][e] + bc.w);
+            *reinterpret_cast<float4 *>(dst + (size_t)(q8 + e) * C + c) = o;
         }
     }
 }
 
+// ---- head (README.md:17-18) -----------------------------------------------------------
 // logits[b,t,k] = sum_c (gT[b,t,c] * sum_v U[b,t,v,c]*gV[b,v,c] / V) * Wh[c,k] + bh[k]
-// one CTA per frame, C threads; K <= 32.  smem: (C/32+1)*K floats
+// One WARP per frame (8 warps, kHeadFrames frames of one clip per CTA); a lane owns 8-channel
+// vectors (16 B of bf16 per load).  gV[b] and the transposed head weights WhT [K][C] are staged
+// in shared memory once per CTA.  C % 8 == 0, K <= 32.
+constexpr int kHeadFrames = 16;
+
+template <typename TU> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 t = __bfloat1622float2(h[e]);
+            f[2 * e] = t.x;
+            f[2 * e + 1] = t.y;
+        }
+    }
+};
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&f)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = d.x; f[5] = d.y; f[6] = d.z; f[7] = d.w;
+    }
+};
+
 template <typename TU, int V>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 head_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const float *__restrict__ gV, int T, int C,
-            int K, const float *__restrict__ Wh, const float *__restrict__ bh, float *__restrict__ logits,
+            int K, const float *__restrict__ WhT, const float *__restrict__ bh, float *__restrict__ logits,
             uint8_t *__restrict__ labels) {
-    extern __shared__ float sm[];       // [nwarps][K]
-    const int bt = blockIdx.x;
-    const int b = bt / T;
-    const int c = threadIdx.x;
-    const int lane = c & 31, warp = c >> 5, nwarps = (blockDim.x + 31) >> 5;
-    float pooled = 0.f;
-    if (c < C) {
-        const TU *row = U + ((size_t)bt * V) * C + c;
-        const float *gv = gV + ((size_t)b * V) * C + c;
-        float acc = 0.f;
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc += ld_act(row + (size_t)v * C) * gv[(size_t)v * C];
-        pooled = acc * gT[(size_t)bt * C + c] / (float)V;
-    }
-    for (int k = 0; k < K; ++k) {
-        float x = c < C ? pooled * Wh[c * K + k] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) sm[warp * K + k] = x;
-    }
+    extern __shared__ __align__(16) float sm[];     // gV[b]: [V][C], then WhT: [K][C]
+    float *sgv = sm, *swh = sm + V * C;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x * 4; e < V * C; e += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(sgv + e) = __ldg(reinterpret_cast<const float4 *>(gV + (size_t)b * V * C + e));
+    for (int e = threadIdx.x * 4; e < K * C; e += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(swh + e) = __ldg(reinterpret_cast<const float4 *>(WhT + e));
     __syncthreads();
-    if (c == 0) {
-        float best = 0.f;
+    for (int t = blockIdx.x * kHeadFrames + warp; t < min(T, (int)(blockIdx.x + 1) * kHeadFrames); t += 8) {
+        const size_t bt = (size_t)b * T + t;
+        float best = 0.f, mine = 0.f;     // lane k keeps logit k
+        for (int cb = 0; cb < C; cb += 256) {      // warp-uniform trip count: lanes past C add zeros
+            const int c0 = cb + lane * 8;
+            const bool on = c0 < C;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            if (on) {
+                const TU *row = U + (bt * V) * C + c0;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    float x[8];
+                    Vec8<TU>::load(row + (size_t)v * C, x);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(sgv + v * C + c0);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(sgv + v * C + c0 + 4);
+                    acc[0] += x[0] * g0.x; acc[1] += x[1] * g0.y; acc[2] += x[2] * g0.z; acc[3] += x[3] * g0.w;
+                    acc[4] += x[4] * g1.x; acc[5] += x[5] * g1.y; acc[6] += x[6] * g1.z; acc[7] += x[7] * g1.w;
+                }
+                float gt[8];
+                Vec8<float>::load(gT + bt * C + c0, gt);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = acc[e] * gt[e] / (float)V;
+            }
+            for (int k = 0; k < K; ++k) {
+                float x = 0.f;
+                if (on) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(swh + k * C + c0);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(swh + k * C + c0 + 4);
+                    x = acc[0] * w0.x + acc[1] * w0.y + acc[2] * w0.z + acc[3] * w0.w + acc[4] * w1.x +
+                        acc[5] * w1.y + acc[6] * w1.z + acc[7] * w1.w;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == k) mine += x;
+            }
+        }
+        if (lane < K) {
+            mine += bh[lane];
+            logits[bt * K + lane] = mine;
+        }
+        // first arg-max over K (ties -> lowest class index), all lanes take part in the shuffles
         int arg = 0;
         for (int k = 0; k < K; ++k) {
-            float acc = bh[k];
-            for (int w = 0; w < nwarps; ++w) acc += sm[w * K + k];
-            logits[(size_t)bt * K + k] = acc;
-            if (k == 0 || acc > best) { best = acc; arg = k; }
+            const float x = __shfl_sync(0xffffffffu, mine, k);
+            if (k == 0 || x > best) { best = x; arg = k; }
         }
-        if (labels) labels[bt] = (uint8_t)arg;
+        if (labels && lane == 0) labels[bt] = (uint8_t)arg;
     }
 }
 
@@ -263,23 +397,25 @@ int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T,
         GS_KERNEL_CHECK();
     }
     {
-        const int threads = ((C + 31) / 32) * 32;
+        const int G = std::max(1, std::min(1024 / C, V));
+        const size_t smem = ((size_t)std::max(G * C, 1024) + C + bp.cs) * sizeof(float);
         {
-            LaunchScope ls(ctx, K_SE, st, 4.0 * B * C * bp.cs, (double)B * T * C * 4);
-            se_kernel<V><<<B, threads, (C + bp.cs) * sizeof(float), st>>>(
-                ctx->PT, ctx->PVpart, T, C, bp.cs, nchunk, bp.seW1, bp.seb1, bp.seW2, bp.seb2, ctx->seS,
-                ctx->PV);
+            LaunchScope ls(ctx, K_SE, st, 4.0 * B * C * bp.cs, (double)B * nchunk * V * C * 4);
+            se_kernel<V><<<B, 1024, smem, st>>>(ctx->PVpart, T, C, bp.cs, nchunk, G, bp.seW1, bp.seb1, bp.seW2,
+                                                bp.seb2, ctx->seS, ctx->PV);
         }
         GS_KERNEL_CHECK();
     }
     {
-        const int threads = ((C + 31) / 32) * 32;
-        dim3 grid(cdiv(T + V, kStjPos), B);
+        const int ntT = cdiv(T, kStjPos);
+        dim3 grid(ntT + cdiv(V, kStjPos), B);
+        const size_t smem = ((size_t)C * kStjLd + (size_t)bp.cj * kStjPos) * sizeof(float);
+        if (smem > 48 * 1024)
+            GS_CUDA(cudaFuncSetAttribute(stj_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             LaunchScope ls(ctx, K_STJ, st, 4.0 * B * (T + V) * C * bp.cj, 2.0 * B * (T + V) * C * 4);
-            stj_kernel<V><<<grid, threads, kStjPos * (C + bp.cj) * sizeof(float), st>>>(
-                ctx->PT, ctx->PV, ctx->seS, T, C, bp.cj, bp.jW, bp.jb, bp.jWt, bp.jbt, bp.jWv, bp.jbv, ctx->gT,
-                ctx->gV);
+            stj_kernel<V><<<grid, 256, smem, st>>>(ctx->PT, ctx->PV, ctx->seS, T, C, bp.cj, ntT, bp.jW, bp.jb,
+                                                   bp.jWt, bp.jbt, bp.jWv, bp.jbv, ctx->gT, ctx->gV);
         }
         GS_KERNEL_CHECK();
     }
@@ -290,11 +426,14 @@ template <typename TU>
 int launch_head(Ctx *ctx, const TU *U, int B, int T, int C, float *logits, uint8_t *labels, cudaStream_t st) {
     constexpr int V = 17;
     const int K = ctx->cfg.num_classes;
-    const int threads = ((C + 31) / 32) * 32;
+    const size_t smem = (size_t)(V + K) * C * sizeof(float);
+    if (smem > 48 * 1024)
+        GS_CUDA(cudaFuncSetAttribute(head_kernel<TU, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(ctx, K_HEAD, st, 2.0 * B * T * C * (V + K), (double)B * T * V * C * sizeof(TU));
-        head_kernel<TU, V><<<B * T, threads, (threads / 32) * K * sizeof(float), st>>>(
-            U, ctx->gT, ctx->gV, T, C, K, ctx->headW, ctx->headb, logits, labels);
+        dim3 grid(cdiv(T, kHeadFrames), B);
+        head_kernel<TU, V><<<grid, 256, smem, st>>>(U, ctx->gT, ctx->gV, T, C, K, ctx->headWT, ctx->headb, logits,
+                                                    labels);
     }
     GS_KERNEL_CHECK();
     return GS_OK;

@@ -133,6 +133,7 @@ int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
     const float *Uprev = nullptr;
     int rc;
     for (int i = 0; i <= last; ++i) {
+        ctx->cur_block = i;
         const BlockParams &bp = ctx->blocks[i];
         float *U = (float *)ctx->bufU[i & 1];
         const size_t items = nframes * bp.cin;
@@ -164,6 +165,7 @@ int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         if ((rc = launch_attention<float>(ctx, bp, U, B, T, st))) return rc;
         Uprev = U;
     }
+    ctx->cur_block = GS_MAX_BLOCKS;
     const int C = ctx->blocks[last].c;
     if (feat_out) return launch_features<float>(ctx, Uprev, B, T, C, feat_out, st);
     return launch_head<float>(ctx, Uprev, B, T, C, logits, labels, st);

@@ -33,7 +33,7 @@ ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
     "gs_compare", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
-    "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_debug_read",
+    "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
 
 
@@ -104,7 +104,9 @@ def load_library():
         L.gs_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p),
                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
-        for name in ("gs_profile_enable", "gs_profile_reset", "gs_profile_read"):
+        L.gs_profile_read_block.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_int64)]
+        for name in ("gs_profile_enable", "gs_profile_reset", "gs_profile_read", "gs_profile_read_block"):
             getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
@@ -199,7 +201,15 @@ class Context:
             _check(self._L.gs_profile_read(self._h, k, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(n),
                                            ctypes.byref(fl), ctypes.byref(by)), "gs_profile_read")
             if n.value:
-                out[name.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+                per_block = {}
+                for blk in range(GS_MAX_BLOCKS + 1):
+                    bms, bn = ctypes.c_double(), ctypes.c_int64()
+                    _check(self._L.gs_profile_read_block(self._h, k, blk, ctypes.byref(bms), ctypes.byref(bn)),
+                           "gs_profile_read_block")
+                    if bn.value:
+                        per_block[blk] = dict(ms=bms.value, launches=bn.value)
+                out[name.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value,
+                                                blocks=per_block)
         return out
 
     def close(self):

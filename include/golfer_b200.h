@@ -146,6 +146,10 @@ int gs_profile_kernels(void);
 int gs_profile_read(gs_ctx *ctx, int kernel, const char **name, double *total_ms,
                     int64_t *launches, double *alg_flops, double *alg_bytes);
 
+/* The same split by network block: `block` in [0, num_blocks) or GS_MAX_BLOCKS for launches
+ * outside any block (head, alignment). */
+int gs_profile_read_block(gs_ctx *ctx, int kernel, int block, double *total_ms, int64_t *launches);
+
 /* Number of kernels this context has launched since creation (bench.py gpu_launches). */
 int64_t gs_launch_count(const gs_ctx *ctx);
 /* Bytes of device workspace currently held by the context. */

@@ -5,7 +5,7 @@ print("roofline", d["roofline"])
 print("whole_net", {k: round(v, 4) for k, v in d["whole_net"].items()})
 for k, v in d["kernels"].items():
     print(f"{k:22s} share {v['share']:.3f} ms/launch {v['ms_per_launch']:.3f} n/step {v['launches_per_step']:.0f} "
-          f"TF {v['tflops']:.1f} GB/s {v['gbs']:.0f}")
+          f"TF {v['tflops']:.1f} GB/s {v['gbs']:.0f}  by block {v.get('ms_per_launch_by_block', {})}")
 if d.get("align"):
     a = d["align"]
     print("align", round(a["value"]), a["unit"], "ms/step", round(a["ms_per_step"], 3), "e2e", round(a["e2e"]["value"]),
