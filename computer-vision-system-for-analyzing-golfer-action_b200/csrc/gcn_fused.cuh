@@ -217,100 +217,108 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
     if (warp == 0) {
         // ===== input-box producer: X box + its gT / gV slices per ring slot =====
-        if (lane == 0) {
-            int slot = 0, tcount = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-                const int b = tile / prm.mtiles;
-                const int mt = tile % prm.mtiles;
-                const int row0 = mt * kRowsPerTile;
-                for (int cb = 0; cb < nbc; ++cb) {
-                    unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
-                    mbar_wait(&x_empty[slot], ph ^ 1);
+        // (whole warp in the loop, one elected lane issues: see tc::elect_one)
+        int slot = 0, tcount = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
+            const int b = tile / prm.mtiles;
+            const int mt = tile % prm.mtiles;
+            const int row0 = mt * kRowsPerTile;
+            for (int cb = 0; cb < nbc; ++cb) {
+                unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
+                mbar_wait(&x_empty[slot], ph ^ 1);
+                if (elect_one()) {
                     GCN_TRACE(0, tcount, cb);
                     mbar_expect_tx(&x_full[slot], kSlotTx);
                     tma_load_3d(sl, &mapX, &x_full[slot], cb * 64, row0, b);
                     tma_load_2d(sl + kGtOff, &mapGT, &x_full[slot], cb * 64, b * prm.T + mt * kFramesPerTile);
                     tma_load_2d(sl + kGvOff, &mapGV, &x_full[slot], cb * 64, b * 17);
-                    if (++slot == XS) { slot = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++slot == XS) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == 3) {
         // ===== weight-ring producer: chunk q = (box cb, partition p) needs WgT[:, p*Cin + cb*64 ..) =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-                for (int q = 0; q < nq; ++q) {
-                    mbar_wait(&w_empty[stage], ph ^ 1);
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+            for (int q = 0; q < nq; ++q) {
+                mbar_wait(&w_empty[stage], ph ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&w_full[stage], lay.w_stage_bytes);
                     tma_load_2d(smem + lay.w_off + (size_t)stage * lay.w_stage_bytes, &mapW, &w_full[stage],
                                 (q % 3) * Cin + (q / 3) * 64, 0);
-                    if (++stage == WS) { stage = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == WS) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc1 = make_idesc_agg();
-            const uint32_t idesc2 = make_idesc_bf16((uint32_t)C);
-            const uint32_t t_d1 = tmem_base + kColD1, t_ab = tmem_base + kColAbig;
-            uint32_t d1_cnt = 0;        // running count of D1 uses
-            uint32_t xa_cnt = 0;        // running count of XA chunks consumed
-            uint32_t acc_cnt = 0;       // running count of tiles (accumulator uses)
-            int wstage = 0, xslot = 0, tcount = 0;
-            uint32_t wph = 0, xph = 0;
-            auto issue_mma2 = [&](int j) {
-                const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
-                const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
-                if (j == 0) mbar_wait(&acc_empty[as], aph ^ 1);   // epilogue has drained this accumulator
-                mbar_wait(&xa_full[slot], ph);
+        // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+        const uint32_t idesc1 = make_idesc_agg();
+        const uint32_t idesc2 = make_idesc_bf16((uint32_t)C);
+        const uint32_t t_d1 = tmem_base + kColD1, t_ab = tmem_base + kColAbig;
+        uint32_t d1_cnt = 0;        // running count of D1 uses
+        uint32_t xa_cnt = 0;        // running count of XA chunks consumed
+        uint32_t acc_cnt = 0;       // running count of tiles (accumulator uses)
+        int wstage = 0, xslot = 0, tcount = 0;
+        uint32_t wph = 0, xph = 0;
+        auto issue_mma2 = [&](int j) {
+            const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
+            const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
+            if (j == 0) mbar_wait(&acc_empty[as], aph ^ 1);   // epilogue has drained this accumulator
+            mbar_wait(&xa_full[slot], ph);
+            mbar_wait(&w_full[wstage], wph);
+            tc_fence_after();
+            const uint64_t da = make_kmajor_desc(smem_u32(smem + lay.xa_off + slot * 16384u), 128);
+            const uint64_t db = make_kmajor_desc(smem_u32(smem + lay.w_off + (size_t)wstage * lay.w_stage_bytes), 128);
+            const uint32_t td = tmem_base + as * (uint32_t)C;
+            if (elect_one()) {
                 GCN_TRACE(1, tcount, 16 + j);
-                mbar_wait(&w_full[wstage], wph);
-                GCN_TRACE(1, tcount, 32 + j);
-                tc_fence_after();
-                const uint64_t da = make_kmajor_desc(smem_u32(smem + lay.xa_off + slot * 16384u), 128);
-                const uint64_t db = make_kmajor_desc(smem_u32(smem + lay.w_off + (size_t)wstage * lay.w_stage_bytes), 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + as * (uint32_t)C, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2,
-                              (uint32_t)((j > 0) | (k > 0)));
+                    umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (uint32_t)((j > 0) | (k > 0)));
                 umma_commit(&xa_empty[slot]);
                 umma_commit(&w_empty[wstage]);
-                ++xa_cnt;
-                if (++wstage == WS) { wstage = 0; wph ^= 1; }
-            };
-            for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-                for (int q = 0; q < nq; ++q) {
-                    const int p = q % 3;
-                    if (p == 0) {
-                        mbar_wait(&x_ready[xslot], xph);      // box gated and visible to the async proxy
-                        tc_fence_after();
-                    }
-                    mbar_wait(d1_empty, (d1_cnt & 1) ^ 1);
-                    GCN_TRACE(1, tcount, q);
+            }
+            __syncwarp();
+            ++xa_cnt;
+            if (++wstage == WS) { wstage = 0; wph ^= 1; }
+        };
+        for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
+            for (int q = 0; q < nq; ++q) {
+                const int p = q % 3;
+                if (p == 0) {
+                    mbar_wait(&x_ready[xslot], xph);      // box gated and visible to the async proxy
                     tc_fence_after();
-                    const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)xslot * kSlotBytes);
+                }
+                mbar_wait(d1_empty, (d1_cnt & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t xb = smem_u32(smem + lay.x_off + (size_t)xslot * kSlotBytes);
+                const uint64_t dx = make_mnmajor_desc(xb);
+                const uint32_t ta = t_ab + (uint32_t)(p * 64);
+                if (elect_one()) {
+                    GCN_TRACE(1, tcount, q);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         // 16 input rows per step: +8 TMEM columns of Abig, +2048 B (two 8-row groups) of X
-                        umma_bf16_ts(t_d1, t_ab + (uint32_t)(p * 64 + k * 8), make_mnmajor_desc(xb + k * 2048), idesc1,
-                                     (uint32_t)(k > 0));
+                        umma_bf16_ts(t_d1, ta + (uint32_t)(k * 8), dx + (uint64_t)(k * 128), idesc1, (uint32_t)(k > 0));
                     }
                     umma_commit(d1_full);
-                    ++d1_cnt;
-                    if (p == 2) {                              // all three MMA1s of this box issued
-                        umma_commit(&x_empty[xslot]);
-                        if (++xslot == XS) { xslot = 0; xph ^= 1; }
-                    }
-                    if (q > 0) issue_mma2(q - 1);
+                    if (p == 2) umma_commit(&x_empty[xslot]);   // all three MMA1s of this box issued
                 }
-                issue_mma2(nq - 1);
-                umma_commit(&acc_full[acc_cnt % (uint32_t)NACC]);
-                ++acc_cnt;
+                __syncwarp();
+                ++d1_cnt;
+                if (p == 2) {
+                    if (++xslot == XS) { xslot = 0; xph ^= 1; }
+                }
+                if (q > 0) issue_mma2(q - 1);
             }
+            issue_mma2(nq - 1);
+            if (elect_one()) umma_commit(&acc_full[acc_cnt % (uint32_t)NACC]);
+            __syncwarp();
+            ++acc_cnt;
         }
     } else if (warp >= 4 && warp < 8) {
         // ===== convert warps: D1 (fp32, TMEM) -> bf16 XA chunk in swizzled smem =====

@@ -99,6 +99,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     printf("tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
+// One lane of a fully active warp.  The single-thread instructions (tcgen05.mma / commit, TMA) are
+// issued under this predicate from WARP-UNIFORM control flow: measured with experiments/mma_probe.cu,
+// the same tcgen05.mma costs ~175 cycles per issue from a `lane == 0` divergent branch (operands
+// shuttled into uniform registers) and runs at the tensor-pipe rate (128 cycles at N=256) this way.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -244,10 +259,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            if (prog.resident) {
-                // weights: every chunk's box once per CTA (stays resident for all tiles)
+        // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+        if (prog.resident) {
+            // weights: every chunk's box once per CTA (stays resident for all tiles)
+            if (elect_one()) {
                 uint32_t total = 0;
                 for (int c = 0; c < prog.nchunks; ++c) total += (uint32_t)prog.b_bytes[prog.ch[c].b_map];
                 mbar_expect_tx(wres, total);
@@ -256,15 +271,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tma_load_2d(smem + prog.w_off + prog.b_off[c], ch.b_map ? &mapB1 : &mapB0, wres, ch.b_k, ch.b_row);
                 }
             }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
-                const int b = tile / prog.mtiles;
-                const int row0 = (tile % prog.mtiles) * kTileM;
-                for (int c = 0; c < prog.nchunks; ++c) {
-                    const Chunk &ch = prog.ch[c];
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char *sa = smem + (size_t)stage * prog.stage_bytes;
+            __syncwarp();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+            const int b = tile / prog.mtiles;
+            const int row0 = (tile % prog.mtiles) * kTileM;
+            for (int c = 0; c < prog.nchunks; ++c) {
+                const Chunk &ch = prog.ch[c];
+                mbar_wait(&empty[stage], phase ^ 1);
+                unsigned char *sa = smem + (size_t)stage * prog.stage_bytes;
+                if (elect_one()) {
                     if (prog.resident) {
                         mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes);
                     } else {
@@ -272,44 +290,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tma_load_2d(sa + prog.a_span, ch.b_map ? &mapB1 : &mapB0, &full[stage], ch.b_k, ch.b_row);
                     }
                     tma_load_3d(sa, ch.a_map ? &mapA1 : &mapA0, &full[stage], ch.a_k, row0 + ch.a_shift, b);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            const uint32_t row_bytes = (uint32_t)prog.kc * 2;
-            const int ksteps = prog.kc / 16;
-            if (prog.resident) mbar_wait(wres, 0);
-            for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t row_bytes = (uint32_t)prog.kc * 2;
+        const int ksteps = prog.kc / 16;
+        if (prog.resident) mbar_wait(wres, 0);
+        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * N);
+            for (int c = 0; c < prog.nchunks; ++c) {
+                const Chunk &ch = prog.ch[c];
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(acc * N);
-                for (int c = 0; c < prog.nchunks; ++c) {
-                    const Chunk &ch = prog.ch[c];
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * prog.stage_bytes);
-                    const uint32_t sb = prog.resident ? smem_u32(smem + prog.w_off + prog.b_off[c]) : sa + prog.a_span;
-                    const uint64_t da = make_kmajor_desc(sa, row_bytes);
-                    const uint64_t db = make_kmajor_desc(sb, row_bytes);
-                    const uint32_t idesc = make_idesc_bf16((uint32_t)ch.n_size);
+                const uint32_t sa = smem_u32(smem + (size_t)stage * prog.stage_bytes);
+                const uint32_t sb = prog.resident ? smem_u32(smem + prog.w_off + prog.b_off[c]) : sa + prog.a_span;
+                const uint64_t da = make_kmajor_desc(sa, row_bytes);
+                const uint64_t db = make_kmajor_desc(sb, row_bytes);
+                const uint32_t idesc = make_idesc_bf16((uint32_t)ch.n_size);
+                const uint32_t td = tacc + (uint32_t)ch.n_off;
+                if (elect_one()) {
                     for (int k = 0; k < ksteps; ++k) {
                         // +32 bytes of K per step: descriptor start address is in 16 B units
-                        umma_bf16(tacc + (uint32_t)ch.n_off, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                   (uint32_t)(ch.accum | (k > 0)));
                     }
                     umma_commit(&empty[stage]);          // frees this smem stage once the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows =====
