@@ -155,7 +155,8 @@ int alloc_workspace(Ctx *ctx) {
     if ((rc = bytes(&ctx->bufR, rows * cmax * esz))) return rc;
     if ((rc = bytes(&ctx->bufU[0], rows * cmax * esz))) return rc;
     if ((rc = bytes(&ctx->bufU[1], rows * cmax * esz))) return rc;
-    const int nchunk = (ctx->max_T + 29) / 30;
+    // pooling partials: 30-frame chunks (stats_kernel) or 7-frame tiles (fused into the bf16 epilogue)
+    const int nchunk = c.precision == GS_PREC_BF16 ? (ctx->max_T + 6) / 7 : (ctx->max_T + 29) / 30;
     if ((rc = dmalloc(ctx, &ctx->PT, frames * cmax))) return rc;
     if ((rc = dmalloc(ctx, &ctx->PV, (size_t)ctx->max_B * c.num_joints * cmax))) return rc;
     if ((rc = dmalloc(ctx, &ctx->PVpart, (size_t)ctx->max_B * nchunk * c.num_joints * cmax))) return rc;

@@ -131,8 +131,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const __grid_constant__ CUtensorMap mapGT, const __grid_constant__ CUtensorMap mapGV,
                  const __grid_constant__ Params prm) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024 B alignment by OFFSET from the __shared__ array (not by integer round-trip of the pointer), so
+    // the compiler keeps the shared address space: LDS/STS instead of generic LD/ST, no false aliasing
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int XS = prm.xslots, WS = prm.wstages, ES = prm.eslots, NACC = prm.nacc;
     const Smem lay = smem_layout(prm.C, XS, WS, ES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar_off);

@@ -21,6 +21,7 @@ namespace gs {
 
 struct BlockMaps {
     CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
+    CUtensorMap u_out7[2], res7;                                 // 7-frame (119-row) boxes: tconv output, its residual
     CUtensorMap f_x_load, f_xg_store, f_y_store, f_gt, f_gv;    // fused GCN kernel (7-frame tiles)
     CUtensorMap wg, w1, w2, wr;
 };
@@ -33,6 +34,7 @@ struct Bf16Path {
     bool fused_gcn = true;      // GOLFER_GCN_UNFUSED=1 selects the SIMT-aggregate + dense-GEMM pair
     bool debug_xa = false;      // GOLFER_DEBUG_XA=1 dumps the fused kernel's XA chunks into bufXA
     unsigned long long *trace = nullptr;   // GOLFER_TRACE_GCN=1: [blocks][5 roles][6 tiles][64 events] clock64
+    unsigned long long *trace_tc = nullptr;   // GOLFER_TRACE_TC=1: [blocks][2 kernels][5 roles][8 tiles][32 events]
 };
 
 namespace {
@@ -169,8 +171,13 @@ int build_maps(Ctx *ctx, int T) {
         if ((rc = tc::make_act_map(&m.y_in, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
         if ((rc = tc::make_act_map(&m.h_out, ctx->bufH, C, rows, batch, 64, tc::kTileM))) return rc;
         if ((rc = tc::make_act_map(&m.h_in, ctx->bufH, C, rows, batch, cr, tc::kTileM))) return rc;
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < 2; ++k) {
             if ((rc = tc::make_act_map(&m.u_out[k], ctx->bufU[k], C, rows, batch, 64, tc::kTileM))) return rc;
+            if ((rc = tc::make_act_map(&m.u_out7[k], ctx->bufU[k], C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
+        }
+        // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
+        if ((rc = tc::make_act_map(&m.res7, i == 0 ? ctx->bufR : ctx->bufX, C, rows, batch, 64, gcn::kRowsPerTile)))
+            return rc;
         if ((rc = tc::make_weight_map(&m.w1, bp->W1T[i], C, C, 64, C))) return rc;
         if ((rc = tc::make_weight_map(&m.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
         if (i > 0) {
@@ -191,12 +198,14 @@ int build_maps(Ctx *ctx, int T) {
     return GS_OK;
 }
 
-void base_program(tc::Program &p, int B, int T, int N, int kc, int relu) {
+void base_program(tc::Program &p, int B, int T, int N, int kc, int relu, int tile_rows = tc::kTileM) {
     memset(&p, 0, sizeof(p));
     p.kc = kc;
     p.N = N;
+    p.T = T;
     p.rows_per_clip = T * V17;
-    p.mtiles = cdiv(p.rows_per_clip, tc::kTileM);
+    p.tile_rows = tile_rows;
+    p.mtiles = cdiv(p.rows_per_clip, tile_rows);
     p.ntiles = B * p.mtiles;
     p.relu = relu;
     p.a_bytes = tc::kTileM * kc * 2;
@@ -204,9 +213,10 @@ void base_program(tc::Program &p, int B, int T, int N, int kc, int relu) {
 
 // Out = relu(In[rows,K] . W^T + bias): K in 64-wide chunks
 int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, const CUtensorMap &out,
-               const float *bias, int B, int T, int K, int N, cudaStream_t st) {
+               const float *bias, int B, int T, int K, int N, cudaStream_t st, unsigned long long *trace = nullptr) {
     tc::Launch L{};
     base_program(L.prog, B, T, N, 64, 1);
+    L.prog.trace = trace;
     L.prog.nchunks = K / 64;
     L.prog.b_bytes[0] = N * 64 * 2;
     for (int k = 0; k < L.prog.nchunks; ++k) {
@@ -217,7 +227,7 @@ int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, c
     }
     L.mapA0 = L.mapA1 = in;
     L.mapB0 = L.mapB1 = w;
-    L.mapOut = out;
+    L.mapOut = L.mapRes = out;
     L.bias = bias;
     const double rows = (double)B * T * V17;
     L.flops = 2.0 * rows * K * N;
@@ -262,6 +272,13 @@ int bf16_path_create(Ctx *ctx) {
             const size_t n = (size_t)GS_MAX_BLOCKS * 5 * gcn::kTraceTiles * gcn::kTraceEv;
             GS_CUDA(cudaMalloc((void **)&bp->trace, n * 8));
             GS_CUDA(cudaMemset(bp->trace, 0, n * 8));
+        }
+    }
+    if (const char *e = getenv("GOLFER_TRACE_TC")) {
+        if (e[0] == '1') {
+            const size_t n = (size_t)GS_MAX_BLOCKS * 2 * 5 * tc::kTraceTiles * tc::kTraceEv;
+            GS_CUDA(cudaMalloc((void **)&bp->trace_tc, n * 8));
+            GS_CUDA(cudaMemset(bp->trace_tc, 0, n * 8));
         }
     }
     const size_t nb = ctx->blocks.size();
@@ -326,6 +343,7 @@ void bf16_path_destroy(Ctx *ctx) {
     for (float *p : bp->bias_t)
         if (p) cudaFree(p);
     if (bp->trace) cudaFree(bp->trace);
+    if (bp->trace_tc) cudaFree(bp->trace_tc);
     delete bp;
     ctx->bf16 = nullptr;
 }
@@ -334,6 +352,7 @@ int bf16_debug_read(Ctx *ctx, const char *name, void *host, size_t nbytes) {
     Bf16Path *bp = ctx->bf16;
     const void *src = nullptr;
     if (bp && !strcmp(name, "gcn_trace")) src = bp->trace;
+    else if (bp && !strcmp(name, "tc_trace")) src = bp->trace_tc;
     else if (!strcmp(name, "XA")) src = ctx->bufXA;
     else if (!strcmp(name, "X")) src = ctx->bufX;
     else if (!strcmp(name, "Y")) src = ctx->bufY;
@@ -413,10 +432,12 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             GS_KERNEL_CHECK();
             if ((rc = dense_gemm(ctx, K_B_GEMM_GCN, m.xa_in, m.wg, m.y_out, b.bg, B, T, 3 * cin, C, st))) return rc;
         }
-        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out, b.b1, B, T, C, C, st))) return rc;
+        const size_t trn = (size_t)5 * tc::kTraceTiles * tc::kTraceEv;
+        unsigned long long *tr = bp->trace_tc ? bp->trace_tc + (size_t)i * 2 * trn : nullptr;
+        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out, b.b1, B, T, C, C, st, tr))) return rc;
         {   // dilated taps (+ residual projection) + residual + ReLU
             tc::Launch L{};
-            base_program(L.prog, B, T, C, cr, 1);
+            base_program(L.prog, B, T, C, cr, 1, gcn::kRowsPerTile);
             const bool proj = (i > 0 && b.has_res);
             int n = 0;
             if (proj) {
@@ -443,18 +464,22 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             L.prog.b_bytes[0] = cr * cr * 2;
             L.prog.b_bytes[1] = C * cr * 2;
             L.prog.has_residual = proj ? 0 : 1;
-            L.residual = proj ? nullptr : (i == 0 ? R0 : X);
+            L.prog.stats = 1;
+            L.prog.trace = tr ? tr + trn : nullptr;
+            L.PT = ctx->PT;
+            L.PVpart = ctx->PVpart;
+            L.mapRes = m.res7;
             L.mapA0 = m.h_in;
             L.mapB0 = m.w2;
             L.mapA1 = proj ? m.xg_in : m.h_in;
             L.mapB1 = proj ? m.wr : m.w2;
-            L.mapOut = m.u_out[i & 1];
+            L.mapOut = m.u_out7[i & 1];
             L.bias = bp->bias_t[i];
             L.flops = 2.0 * rows * (3.0 * cr * C + (proj ? (double)cin * C : 0.0));
             L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
             if ((rc = tc::launch(ctx, K_B_TCONV, L, st))) return rc;
         }
-        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st))) return rc;
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, gcn::kFramesPerTile))) return rc;
         Uprev = U;
     }
     ctx->cur_block = GS_MAX_BLOCKS;

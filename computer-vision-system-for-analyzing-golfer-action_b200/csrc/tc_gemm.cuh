@@ -14,12 +14,18 @@
 //     fused with the residual projection (extra chunks, K = Cin, N = C) and the final add+ReLU.
 // Stages replaced: /root/reference/README.md:27-30.
 //
-// Warp roles (256 threads, persistent over (clip, row-tile) tiles, 1 CTA per SM):
-//   warp 0  TMA producer      warp 1  tcgen05.mma issuer (one elected lane)
-//   warp 2  TMEM allocator    warps 4-7  epilogue: tcgen05.ld -> bias/residual/ReLU -> bf16 ->
-//                                        swizzled smem -> TMA store
-// Pipelines: smem ring (full/empty mbarriers) and a double-buffered TMEM accumulator
-// (tmem_full/tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (640 threads, persistent over (clip, row-tile) tiles, 1 CTA per SM):
+//   warp 0  TMA producer (A boxes, streamed weights)     warp 1  tcgen05.mma issuer
+//   warp 2  TMEM allocator, then residual-box TMA producer of group 1      warp 3  ... of group 0
+//   warps 4-11 / 12-19  two epilogue groups of 8 warps; group g drains accumulator buffer g, so two
+//           tiles are in their epilogues at once.  Warps w and w+4 of a group share TMEM lanes (tile
+//           rows) and split each 64-column box in halves:  tcgen05.ld -> +bias (+residual read from
+//           the TMA-loaded box in the staging slot) -> ReLU -> bf16 written back IN PLACE to the
+//           swizzled slot -> TMA store; optionally the clip-pooling partial sums (PT / PVpart of
+//           segment_common.cuh) are taken from the staged tile before it leaves.
+// Pipelines: smem ring (full/empty mbarriers), double-buffered TMEM accumulator (tfull/tempty),
+// per-group staging slots (res_full/res_empty).  Measured (profiles/): with 4 epilogue warps the
+// epilogue (1700 cycles per 64-column box) bounded every N=256 launch, not HBM or the tensor pipe.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
@@ -31,7 +37,8 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kMaxChunks = 32;
-constexpr int kThreads = 256;
+constexpr int kThreads = 640;
+constexpr int kGroupThreads = 256;   // one epilogue group: 8 warps
 
 struct Chunk {
     int a_map;    // 0 / 1: which A tensor map
@@ -53,7 +60,11 @@ struct Program {
     int ntiles;         // total tiles = B * mtiles
     int rows_per_clip;  // T * V
     int relu;
-    int has_residual;   // add residual[b, r, n] (bf16, row stride N) before the activation
+    int has_residual;   // add residual[b, r, n] (bf16, TMA-loaded through mapRes) before the activation
+    int tile_rows;      // output rows per tile: 128, or 119 (7 whole frames) when stats are taken
+    int stats;          // 1: write PT[b,t,n] (sum over joints) and PVpart[b,tile,v,n] (sum over the tile's frames)
+    int T;              // frames per clip (stats)
+    unsigned long long *trace;   // optional clock64 trace of CTA 0: [5 roles][kTraceTiles][kTraceEv] (tools/trace_tc.py)
     int a_bytes;        // bytes of one A box
     int b_bytes[2];     // bytes of one B box per B map
     // shared-memory plan (host: plan_smem)
@@ -211,22 +222,33 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
 }
 
 constexpr int kMaxStages = 8;
+constexpr int kTraceTiles = 8, kTraceEv = 32;
+#define TC_TRACE(role, tcount, ev)                                                                        \
+    do {                                                                                                  \
+        if (prog.trace && blockIdx.x == 0 && (tcount) < kTraceTiles && (ev) < kTraceEv)                    \
+            prog.trace[((role)*kTraceTiles + (tcount)) * kTraceEv + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
-               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ Program prog,
-               const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual) {
+               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
+               const __grid_constant__ Program prog, const float *__restrict__ bias,
+               float *__restrict__ PT, float *__restrict__ PVpart) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024 B alignment by OFFSET from the __shared__ array (not by integer round-trip of the pointer), so
+    // the compiler keeps the shared address space: LDS/STS instead of generic LD/ST, no false aliasing
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int STAGES = prog.stages, ES = prog.eslots;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + prog.bar_off);
     uint64_t *empty = full + kMaxStages;
     uint64_t *tfull = empty + kMaxStages;
     uint64_t *tempty = tfull + 2;
     uint64_t *wres = tempty + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wres + 1);
+    uint64_t *res_full = wres + 1;          // [2 groups][2 slots]
+    uint64_t *res_empty = res_full + 4;     // [2 groups][2 slots]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_empty + 4);
+    float *sbias = reinterpret_cast<float *>(smem + prog.bar_off + 512);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -239,6 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapB0);
         tma_prefetch_desc(&mapB1);
         tma_prefetch_desc(&mapOut);
+        tma_prefetch_desc(&mapRes);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
@@ -247,12 +270,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 1);
+            mbar_init(&tempty[s], kGroupThreads);     // every thread of the draining epilogue group arrives
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&res_full[s], 1);
+            mbar_init(&res_empty[s], 1);
         }
         mbar_init(wres, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    for (int k = threadIdx.x; k < N; k += kThreads) sbias[k] = bias[k];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -273,16 +301,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             __syncwarp();
         }
-        int stage = 0;
+        int stage = 0, tcount = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x, ++tcount) {
             const int b = tile / prog.mtiles;
-            const int row0 = (tile % prog.mtiles) * kTileM;
+            const int row0 = (tile % prog.mtiles) * prog.tile_rows;
             for (int c = 0; c < prog.nchunks; ++c) {
                 const Chunk &ch = prog.ch[c];
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *sa = smem + (size_t)stage * prog.stage_bytes;
                 if (elect_one()) {
+                    TC_TRACE(0, tcount, c);
                     if (prog.resident) {
                         mbar_expect_tx(&full[stage], (uint32_t)prog.a_bytes);
                     } else {
@@ -304,7 +333,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t row_bytes = (uint32_t)prog.kc * 2;
         const int ksteps = prog.kc / 16;
         if (prog.resident) mbar_wait(wres, 0);
-        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x, ++tcount) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(acc * N);
@@ -319,6 +349,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t idesc = make_idesc_bf16((uint32_t)ch.n_size);
                 const uint32_t td = tacc + (uint32_t)ch.n_off;
                 if (elect_one()) {
+                    TC_TRACE(1, tcount, c);
                     for (int k = 0; k < ksteps; ++k) {
                         // +32 bytes of K per step: descriptor start address is in 16 B units
                         umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
@@ -329,54 +360,97 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (elect_one()) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+            if (elect_one()) {
+                TC_TRACE(1, tcount, 31);
+                umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+            }
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+    } else if (warp == 2 || warp == 3) {
+        // ===== residual producers (warp 3 -> group 0, warp 2 -> group 1): one 64-column box of the
+        // residual per epilogue box, straight into the group's staging slot (the epilogue adds it and
+        // overwrites it in place).  One warp per group so neither group ever waits for the other's slots.
+        if (prog.has_residual) {
+            const int g = 3 - warp;
+            uint32_t ecnt = 0;
+            const uint32_t box_bytes = (uint32_t)prog.tile_rows * 128u;
+            int it = g;
+            for (int tile = blockIdx.x + g * gridDim.x; tile < prog.ntiles; tile += 2 * gridDim.x, it += 2) {
+                const int b = tile / prog.mtiles;
+                const int row0 = (tile % prog.mtiles) * prog.tile_rows;
+                for (int q = 0; q < N / 64; ++q) {
+                    const uint32_t sl = ecnt % (uint32_t)ES, ph = (ecnt / (uint32_t)ES) & 1;
+                    uint64_t *rf = &res_full[g * 2 + (int)sl];
+                    mbar_wait(&res_empty[g * 2 + (int)sl], ph ^ 1);
+                    if (elect_one()) {
+                        TC_TRACE(2, it, q);
+                        mbar_expect_tx(rf, box_bytes);
+                        tma_load_3d(smem + prog.out_off + (size_t)(g * ES + (int)sl) * (kTileM * 128), &mapRes, rf, q * 64,
+                                    row0, b);
+                    }
+                    __syncwarp();
+                    ++ecnt;
+                }
+            }
+        }
     } else if (warp >= 4) {
-        // ===== epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows =====
-        const int ew = warp - 4;
+        // ===== epilogue: two groups of 8 warps; warp w owns TMEM lanes [32(w%4), +32) = tile rows and
+        // columns [32h, 32h+32) of each 64-column box, h = (w-4)/4 % 2 =====
+        const int g = (warp - 4) >> 3;                 // group = accumulator buffer
+        const int ew = (warp - 4) & 3;
+        const int half = ((warp - 4) >> 2) & 1;
+        const int gt = threadIdx.x - 128 - g * kGroupThreads;    // thread inside the group, 0..255
         const int r = ew * 32 + lane;                  // row inside the tile
-        const bool leader = (threadIdx.x == 128);
-        unsigned char *sout = smem + prog.out_off;
-        int acc = 0;
-        uint32_t acc_phase = 0, ecnt = 0;
-        for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x) {
+        const bool leader = (gt == 0);
+        const int bar_id = 1 + g;
+        unsigned char *sout = smem + prog.out_off + (size_t)(g * ES) * (kTileM * 128);
+        uint32_t ecnt = 0;
+        int pending = -1;                               // slot whose TMA store has not been drained yet (leader)
+        int it = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < prog.ntiles; tile += 2 * gridDim.x, it += 2) {
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
             const int b = tile / prog.mtiles;
-            const int row0 = (tile % prog.mtiles) * kTileM;
-            mbar_wait(&tfull[acc], acc_phase);
+            const int mt = tile % prog.mtiles;
+            const int row0 = mt * prog.tile_rows;
+            mbar_wait(&tfull[g], acc_phase);
+            if (leader) TC_TRACE(3 + g, it >> 1, 0);
             tc_fence_after();
-            const bool row_ok = (row0 + r) < prog.rows_per_clip;
-            const __nv_bfloat16 *res_row =
-                residual + ((size_t)b * prog.rows_per_clip + (size_t)(row0 + r)) * (size_t)N;
             for (int q = 0; q < N / 64; ++q) {
-                uint32_t v[64];
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N + q * 64);
-                tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                const uint32_t es = ecnt % (uint32_t)ES, eph = (ecnt / (uint32_t)ES) & 1;
+                unsigned char *box = sout + (size_t)es * (kTileM * 128);
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(g * N + q * 64 + half * 32);
+                tmem_ld32(taddr, v);
+                if (prog.has_residual) {
+                    mbar_wait(&res_full[g * 2 + (int)es], eph);   // slot is ours and holds the residual box
+                } else if (ES == 1) {
+                    // single slot, no producer: the leader drained the previous store after issuing it
+                    asm volatile("bar.sync %0, 256;" ::"r"(bar_id + 2) : "memory");
+                }
+                if (leader) TC_TRACE(3 + g, it >> 1, 1 + 4 * q);
                 tmem_ld_wait();
+                if (leader) TC_TRACE(3 + g, it >> 1, 2 + 4 * q);
                 if (q == N / 64 - 1) {
                     // every TMEM read of this accumulator is done: hand it back to the MMA warp
                     tc_fence_before();
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (leader) mbar_arrive(&tempty[acc]);
+                    mbar_arrive(&tempty[g]);
                 }
-                // staging slot reuse: the TMA store issued ES boxes ago must have finished reading it
-                const uint32_t es = ecnt % (uint32_t)ES;
-                if (leader && ecnt >= (uint32_t)ES) {
-                    if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                unsigned char *box = sout + (size_t)es * (kTileM * 128);
+                unsigned char *rowp = box + (size_t)r * 128;
+                const float *bq = sbias + q * 64 + half * 32;
 #pragma unroll
-                for (int cchunk = 0; cchunk < 8; ++cchunk) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bq + cc * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bq + cc * 8 + 4);
                     float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        f[e] = __uint_as_float(v[cchunk * 8 + e]) + __ldg(bias + q * 64 + cchunk * 8 + e);
-                    if (prog.has_residual && row_ok) {
-                        const uint4 rr = *reinterpret_cast<const uint4 *>(res_row + q * 64 + cchunk * 8);
+                    f[0] = __uint_as_float(v[cc * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[cc * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[cc * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[cc * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[cc * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[cc * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[cc * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[cc * 8 + 7]) + b1.w;
+                    // 128B-swizzled box row: 16 B chunk index XOR (row & 7) — matches the TMA maps
+                    uint4 *sp = reinterpret_cast<uint4 *>(rowp + (((half * 4 + cc) ^ (r & 7)) << 4));
+                    if (prog.has_residual) {
+                        const uint4 rr = *sp;
                         const __nv_bfloat162 *rp = reinterpret_cast<const __nv_bfloat162 *>(&rr);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -393,20 +467,84 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     __nv_bfloat162 *pp = reinterpret_cast<__nv_bfloat162 *>(&packed);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                    // 128B-swizzled box row: 16 B chunk index XOR (row & 7) — matches the TMA map
-                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cchunk ^ (r & 7)) << 4)) = packed;
+                    *sp = packed;
                 }
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // two slots, no producer: the store issued a whole box ago (the only one pending) must have
+                // read its slot before the NEXT box overwrites it; that box starts after this barrier
+                if (leader && !prog.has_residual && ES == 2) tma_store_wait_read0();
+                asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
                 if (leader) {
+                    TC_TRACE(3 + g, it >> 1, 3 + 4 * q);
                     tma_store_3d(&mapOut, box, q * 64, row0, b);
                     tma_store_commit();
+                    if (!prog.has_residual) {
+                        if (ES == 1) tma_store_wait_read0();   // published to the group by the next box's barrier
+                    } else {
+                        // the previous box's store has had a whole box period: drain it and hand its slot back
+                        // (every thread finished its pooling reads of that box before this box's barrier)
+                        if (pending >= 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            mbar_arrive(&res_empty[g * 2 + pending]);
+                        }
+                        pending = (int)es;
+                    }
                 }
+                if (leader) TC_TRACE(3 + g, it >> 1, 17 + 2 * q);
+                if (prog.stats) {
+                    // clip-pooling partial sums from the staged bf16 tile (7 frames x 17 joints x 64 channels):
+                    // thread = (channel pair c2, part); frames / joints are split over the 8 parts
+                    const int c2 = gt & 31, part = gt >> 5;
+                    const int nfv = min(7, prog.T - mt * 7);                 // valid frames of this tile
+                    const uint32_t coff = (uint32_t)(c2 & 3) * 4u;
+                    const int cchunk = c2 >> 2;
+                    const unsigned char *colp = box + coff;
+                    auto ldv = [&](int row) {
+                        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(
+                            colp + (size_t)row * 128 + ((cchunk ^ (row & 7)) << 4)));
+                    };
+                    // frame sums: part p (< 7) owns frame p
+                    if (part < nfv) {
+                        float2 t[17];
+#pragma unroll
+                        for (int vv = 0; vv < 17; ++vv) t[vv] = ldv(part * 17 + vv);
+                        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int vv = 0; vv < 17; ++vv) {
+                            acc.x += t[vv].x;
+                            acc.y += t[vv].y;
+                        }
+                        *reinterpret_cast<float2 *>(PT + ((size_t)b * prog.T + (size_t)(mt * 7 + part)) * N + q * 64 + 2 * c2) = acc;
+                    }
+                    if (leader) TC_TRACE(3 + g, it >> 1, 18 + 2 * q);
+                    // joint sums over the tile's frames: part p owns joints p, p+8, p+16
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int vv = part + 8 * k;
+                        if (vv < 17) {
+                            float2 t[7];
+#pragma unroll
+                            for (int f = 0; f < 7; ++f) t[f] = ldv(f * 17 + vv);
+                            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int f = 0; f < 7; ++f)
+                                if (f < nfv) {
+                                    acc.x += t[f].x;
+                                    acc.y += t[f].y;
+                                }
+                            *reinterpret_cast<float2 *>(PVpart + (((size_t)b * prog.mtiles + mt) * 17 + vv) * N + q * 64 + 2 * c2) = acc;
+                        }
+                    }
+                }
+                if (leader) TC_TRACE(3 + g, it >> 1, 4 + 4 * q);
                 ++ecnt;
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (leader) tma_store_wait_all0();
+        if (leader) {
+            tma_store_wait_read0();
+            if (pending >= 0) mbar_arrive(&res_empty[g * 2 + pending]);
+            tma_store_wait_all0();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -506,64 +644,58 @@ inline int make_f32_map(CUtensorMap *m, const void *base, int width, long long n
 }
 
 struct Launch {
-    CUtensorMap mapA0, mapA1, mapB0, mapB1, mapOut;
+    CUtensorMap mapA0, mapA1, mapB0, mapB1, mapOut, mapRes;   // mapRes: residual boxes (has_residual)
     Program prog;
     const float *bias = nullptr;
-    const __nv_bfloat16 *residual = nullptr;
+    float *PT = nullptr, *PVpart = nullptr;                    // prog.stats outputs
     double flops = 0, bytes = 0;   // algorithmic, for the profiler
 };
 
-// Fill the shared-memory plan of `p` (nchunks, kc, N, a_bytes, b_bytes, ch[] must be set).
+// Fill the shared-memory plan of `p` (nchunks, kc, N, a_bytes, b_bytes, ch[], stats must be set).
 // Weights stay resident when they fit next to >= 3 A stages; otherwise they stream with A.
+// Staging: 2 epilogue groups x eslots 16 KB boxes (the pooling sums need eslots = 2).
 inline bool plan_smem(Program &p, bool allow_resident = true) {
     const uint32_t limit = 227u * 1024u;
     const uint32_t a_span = ((uint32_t)p.a_bytes + 1023u) & ~1023u;
-    const uint32_t bars = 512, slack = 1024;
+    const uint32_t bars = 512 + 1024, slack = 1024;   // barriers + bias[N <= 256]
     uint32_t wtotal = 0;
     for (int c = 0; c < p.nchunks; ++c) {
         p.b_off[c] = wtotal;
         wtotal += ((uint32_t)p.b_bytes[p.ch[c].b_map] + 1023u) & ~1023u;
-    }
-    const int es_c[2] = {2, 1};
-    if (allow_resident) {
-        for (int es : es_c)
-            for (int st = kMaxStages; st >= 3; --st) {
-                const uint32_t tot = wtotal + a_span * st + (uint32_t)es * 16384u + bars + slack;
-                if (tot <= limit) {
-                    p.resident = 1;
-                    p.stages = st;
-                    p.eslots = es;
-                    p.a_span = a_span;
-                    p.stage_bytes = a_span;
-                    p.w_off = a_span * st;
-                    p.out_off = p.w_off + wtotal;
-                    p.bar_off = p.out_off + (uint32_t)es * 16384u;
-                    p.smem_total = p.bar_off + bars + slack;
-                    return true;
-                }
-            }
     }
     uint32_t bmax = 0;
     for (int c = 0; c < p.nchunks; ++c) {
         const uint32_t b = ((uint32_t)p.b_bytes[p.ch[c].b_map] + 1023u) & ~1023u;
         bmax = b > bmax ? b : bmax;
     }
-    for (int es : es_c)
-        for (int st = kMaxStages; st >= 2; --st) {
-            const uint32_t tot = (a_span + bmax) * st + (uint32_t)es * 16384u + bars + slack;
-            if (tot <= limit) {
-                p.resident = 0;
-                p.stages = st;
-                p.eslots = es;
-                p.a_span = a_span;
-                p.stage_bytes = a_span + bmax;
-                p.w_off = 0;
-                p.out_off = p.stage_bytes * st;
-                p.bar_off = p.out_off + (uint32_t)es * 16384u;
-                p.smem_total = p.bar_off + bars + slack;
+    auto fill = [&](int resident, int st, int es) {
+        p.resident = resident;
+        p.stages = st;
+        p.eslots = es;
+        p.a_span = a_span;
+        p.stage_bytes = resident ? a_span : a_span + bmax;
+        p.w_off = resident ? a_span * st : 0;
+        p.out_off = resident ? p.w_off + wtotal : p.stage_bytes * st;
+        p.bar_off = p.out_off + 2u * (uint32_t)es * 16384u;
+        p.smem_total = p.bar_off + bars + slack;
+    };
+    const int es_hi = 2, es_lo = (p.stats || p.has_residual) ? 2 : 1;
+    // preference: resident weights with a deep A ring; give up staging depth before ring depth
+    if (allow_resident) {
+        for (int want : {4, 3})
+            for (int es = es_hi; es >= es_lo; --es)
+                for (int st = kMaxStages; st >= want; --st)
+                    if (wtotal + a_span * st + 2u * es * 16384u + bars + slack <= limit) {
+                        fill(1, st, es);
+                        return true;
+                    }
+    }
+    for (int es = es_hi; es >= es_lo; --es)
+        for (int st = kMaxStages; st >= 2; --st)
+            if ((a_span + bmax) * st + 2u * es * 16384u + bars + slack <= limit) {
+                fill(0, st, es);
                 return true;
             }
-        }
     return false;
 }
 
@@ -579,8 +711,8 @@ inline int launch(Ctx *ctx, int kid, Launch &L, cudaStream_t st) {
     GS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.prog.smem_total));
     {
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
-        tc_gemm_kernel<<<grid, kThreads, L.prog.smem_total, st>>>(L.mapA0, L.mapA1, L.mapB0, L.mapB1, L.mapOut, L.prog,
-                                                                  L.bias, L.residual);
+        tc_gemm_kernel<<<grid, kThreads, L.prog.smem_total, st>>>(L.mapA0, L.mapA1, L.mapB0, L.mapB1, L.mapOut, L.mapRes,
+                                                                  L.prog, L.bias, L.PT, L.PVpart);
     }
     GS_KERNEL_CHECK();
     return GS_OK;

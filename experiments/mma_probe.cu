@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "gcn_fused.cuh"
 
 namespace gs {
@@ -24,24 +26,13 @@ __device__ __forceinline__ uint64_t desc_kmajor_bo(uint32_t smem_addr, uint32_t 
     return make_kmajor_desc(smem_addr, row_bytes) | ((uint64_t)(base_off & 7) << 49);
 }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "elect.sync _|P1, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 struct Result {
     long long cyc[32][4];   // [test][0: issue cycles, 1: total cycles, 2: reps]
     int mism[8][4];         // [shift idx][variant]
+    int chain[8];           // f16 TMEM-chain variants: mismatches (or -1 = not run)
 };
 
-__global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps) {
+__global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps, int vmask) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -62,6 +53,17 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps) {
         const int chunk = k / 8, within = k % 8;
         __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(sB + n * 128 + ((chunk ^ (n & 7)) << 4)) + within;
         *p = __float2bfloat16_rn(n == k ? 1.f : 0.f);
+    }
+    unsigned char *sA16 = sB + 256 * 128;   // 128 rows x 128 B, f16 copy of A rows 0..127
+    unsigned char *sB16 = sA16 + 128 * 128; // 64 rows x 128 B, f16 identity
+    for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+        const int r = e / 64, k = e % 64;
+        __half *p = reinterpret_cast<__half *>(sA16 + r * 128 + (((k / 8) ^ (r & 7)) << 4)) + (k % 8);
+        *p = __float2half_rn((float)((r * 64 + k) % 251));
+        if (r < 64) {
+            __half *q = reinterpret_cast<__half *>(sB16 + r * 128 + (((k / 8) ^ (r & 7)) << 4)) + (k % 8);
+            *q = __float2half_rn(r == k ? 1.f : 0.f);
+        }
     }
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -247,18 +249,69 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps) {
             tc_fence_after();
         }
     }
+    // ---------------- (C) f16 accumulator of MMA-a re-used in place as the TMEM A operand of MMA-b ----------------
+    // variant bit0: operands of MMA-a are f16 (else bf16); bit1: B of MMA-b is f16 (else bf16)
+    for (int variant = 0; variant < 4; ++variant) {
+        if (!((vmask >> variant) & 1)) {
+            if (threadIdx.x == 0) out->chain[variant] = -1;
+            continue;
+        }
+        const bool a16 = variant & 1, b16 = variant & 2;
+        if (warp == 1) {
+            const uint32_t fa = a16 ? 0u : 1u, fb = b16 ? 0u : 1u;
+            // idesc: c_format [4,6) (0 = f16, 1 = f32), a_format [7,10), b_format [10,13), N>>3 at 17, M>>4 at 24
+            const uint32_t id_a = (0u << 4) | (fa << 7) | (fa << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t id_b = (1u << 4) | (0u << 7) | (fb << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t da = make_kmajor_desc(smem_u32(a16 ? sA16 : sA), 128);
+            const uint64_t db1 = make_kmajor_desc(smem_u32(a16 ? sB16 : sB), 128);
+            const uint64_t db2 = make_kmajor_desc(smem_u32(b16 ? sB16 : sB), 128);
+            if (elect_one()) {
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), id_a, (uint32_t)(k > 0));
+                umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ts(tmem, tmem + 256 + (uint32_t)(k * 8), db2 + (uint64_t)(2 * k), id_b, (uint32_t)(k > 0));
+                umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, phase ^ 1);
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp >= 4) {
+            uint32_t v[64];
+            const int m = (warp - 4) * 32 + lane;
+            const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+            tmem_ld32(tmem + lane_base, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld32(tmem + lane_base + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_ld_wait();
+            int bad = 0;
+            for (int n = 0; n < 64; ++n)
+                if (__uint_as_float(v[n]) != (float)((m * 64 + n) % 251)) ++bad;
+            if (bad) atomicAdd(&out->chain[variant], bad);
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 int main(int argc, char **argv) {
     const int reps = argc > 1 ? atoi(argv[1]) : 64;
     const int grid = argc > 2 ? atoi(argv[2]) : 1;
+    const int vmask = argc > 3 ? atoi(argv[3]) : 0;
     Result *d;
     cudaMalloc(&d, sizeof(Result));
     cudaMemset(d, 0, sizeof(Result));
-    const int smem = 384 * 128 + 256 * 128 + 1024;
+    const int smem = 384 * 128 + 256 * 128 + 128 * 128 + 64 * 128 + 1024;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe_kernel<<<grid, 256, smem>>>(d, reps);
+    probe_kernel<<<grid, 256, smem>>>(d, reps, vmask);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("CUDA error: %s\n", cudaGetErrorString(e));
@@ -281,5 +334,8 @@ int main(int argc, char **argv) {
     for (int si = 0; si < 8; ++si)
         printf("row shift %2d: mismatches base_offset=0: %5d   =s%%8: %5d   =(8-s)%%8: %5d\n", shifts[si], h.mism[si][0],
                h.mism[si][1], h.mism[si][2]);
+    for (int v = 0; v < 4; ++v)
+        printf("f16 TMEM chain, MMA-a operands %s, MMA-b B %s: mismatches %d\n", (v & 1) ? "f16 " : "bf16", (v & 2) ? "f16 " : "bf16",
+               h.chain[v]);
     return 0;
 }
