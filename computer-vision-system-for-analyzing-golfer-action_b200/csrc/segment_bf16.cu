@@ -15,13 +15,15 @@
 #include "segment_common.cuh"
 #include "tc_gemm.cuh"
 #include "gcn_fused.cuh"
+#include "tconv_window.cuh"
 #include <stdlib.h>
 
 namespace gs {
 
 struct BlockMaps {
     CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
-    CUtensorMap u_out7[2], res7;                                 // 7-frame (119-row) boxes: tconv output, its residual
+    CUtensorMap h_out_jm;                                        // 1x1 GEMM store into joint-major H [B,V,T,C]
+    tw::Maps tw;                                                 // sliding-window temporal conv
     CUtensorMap f_x_load, f_xg_store, f_y_store, f_gt, f_gv;    // fused GCN kernel (7-frame tiles)
     CUtensorMap wg, w1, w2, wr;
 };
@@ -171,13 +173,26 @@ int build_maps(Ctx *ctx, int T) {
         if ((rc = tc::make_act_map(&m.y_in, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
         if ((rc = tc::make_act_map(&m.h_out, ctx->bufH, C, rows, batch, 64, tc::kTileM))) return rc;
         if ((rc = tc::make_act_map(&m.h_in, ctx->bufH, C, rows, batch, cr, tc::kTileM))) return rc;
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 2; ++k)
             if ((rc = tc::make_act_map(&m.u_out[k], ctx->bufU[k], C, rows, batch, 64, tc::kTileM))) return rc;
-            if ((rc = tc::make_act_map(&m.u_out7[k], ctx->bufU[k], C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
+        {   // temporal conv: joint-major H, window loads, (C,V,T,B) views of the [B,T,V,C] tensors
+            int dmax = 1;
+            for (int r = 0; r < R; ++r) dmax = dmax > ctx->cfg.dilations[r] ? dmax : ctx->cfg.dilations[r];
+            const bool proj = (i > 0 && b.has_res);
+            if ((rc = tw::make_bvtc_map(&m.h_out_jm, ctx->bufH, C, T, batch, true, 64, gcn::kFramesPerTile))) return rc;
+            if ((rc = tw::make_bvtc_map(&m.tw.h_win, ctx->bufH, C, T, batch, false, 64, tw::kFramesTile + 2 * dmax))) return rc;
+            if ((rc = tw::make_btvc_joint_map(&m.tw.out, ctx->bufU[i & 1], C, T, batch, 64, tw::kFramesTile))) return rc;
+            // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
+            if ((rc = tw::make_btvc_joint_map(&m.tw.res, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, tw::kFramesTile)))
+                return rc;
+            m.tw.xg = m.tw.res;
+            if ((rc = tc::make_weight_map(&m.tw.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
+            m.tw.wr = m.tw.w2;
+            if (proj) {
+                if ((rc = tw::make_btvc_joint_map(&m.tw.xg, ctx->bufX, cin, T, batch, 64, tw::kFramesTile))) return rc;
+                if ((rc = tc::make_weight_map(&m.tw.wr, bp->WrT[i], cin, C, 64, 64))) return rc;
+            }
         }
-        // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
-        if ((rc = tc::make_act_map(&m.res7, i == 0 ? ctx->bufR : ctx->bufX, C, rows, batch, 64, gcn::kRowsPerTile)))
-            return rc;
         if ((rc = tc::make_weight_map(&m.w1, bp->W1T[i], C, C, 64, C))) return rc;
         if ((rc = tc::make_weight_map(&m.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
         if (i > 0) {
@@ -213,10 +228,12 @@ void base_program(tc::Program &p, int B, int T, int N, int kc, int relu, int til
 
 // Out = relu(In[rows,K] . W^T + bias): K in 64-wide chunks
 int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, const CUtensorMap &out,
-               const float *bias, int B, int T, int K, int N, cudaStream_t st, unsigned long long *trace = nullptr) {
+               const float *bias, int B, int T, int K, int N, cudaStream_t st, unsigned long long *trace = nullptr,
+               bool out_joint_major = false) {
     tc::Launch L{};
-    base_program(L.prog, B, T, N, 64, 1);
+    base_program(L.prog, B, T, N, 64, 1, out_joint_major ? gcn::kRowsPerTile : tc::kTileM);
     L.prog.trace = trace;
+    L.prog.out_joint_major = out_joint_major ? 1 : 0;
     L.prog.nchunks = K / 64;
     L.prog.b_bytes[0] = N * 64 * 2;
     for (int k = 0; k < L.prog.nchunks; ++k) {
@@ -434,52 +451,35 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         }
         const size_t trn = (size_t)5 * tc::kTraceTiles * tc::kTraceEv;
         unsigned long long *tr = bp->trace_tc ? bp->trace_tc + (size_t)i * 2 * trn : nullptr;
-        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out, b.b1, B, T, C, C, st, tr))) return rc;
-        {   // dilated taps (+ residual projection) + residual + ReLU
-            tc::Launch L{};
-            base_program(L.prog, B, T, C, cr, 1, gcn::kRowsPerTile);
+        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out_jm, b.b1, B, T, C, C, st, tr, true))) return rc;
+        {   // dilated taps (+ residual projection) + residual + ReLU + pooling sums (tconv_window.cuh)
+            tw::LaunchTw L{};
+            L.maps = m.tw;
+            tw::Params &q = L.prm;
+            memset(&q, 0, sizeof(q));
             const bool proj = (i > 0 && b.has_res);
-            int n = 0;
-            if (proj) {
-                for (int k = 0; k < cin / cr; ++k) {
-                    tc::Chunk &c = L.prog.ch[n++];
-                    c.a_map = 1;
-                    c.b_map = 1;
-                    c.a_k = c.b_k = k * cr;
-                    c.n_size = C;
-                    c.accum = k > 0;
-                }
+            q.B = B; q.T = T; q.C = C; q.cr = cr; q.cin = cin;
+            q.nbr = 64 / cr;
+            q.proj = proj ? 1 : 0;
+            q.nkx = proj ? cin / 64 : 0;
+            q.dmax = 1;
+            for (int r = 0; r < R; ++r) {
+                q.dil[r] = ctx->cfg.dilations[r];
+                q.dmax = q.dmax > q.dil[r] ? q.dmax : q.dil[r];
             }
-            for (int r = 0; r < R; ++r)
-                for (int j = 0; j < 3; ++j) {
-                    tc::Chunk &c = L.prog.ch[n++];
-                    c.a_k = r * cr;
-                    c.a_shift = (j - 1) * ctx->cfg.dilations[r] * V17;
-                    c.b_row = (r * 3 + j) * cr;
-                    c.n_off = r * cr;
-                    c.n_size = cr;
-                    c.accum = proj || j > 0;
-                }
-            L.prog.nchunks = n;
-            L.prog.b_bytes[0] = cr * cr * 2;
-            L.prog.b_bytes[1] = C * cr * 2;
-            L.prog.has_residual = proj ? 0 : 1;
-            L.prog.stats = 1;
-            L.prog.trace = tr ? tr + trn : nullptr;
-            L.PT = ctx->PT;
-            L.PVpart = ctx->PVpart;
-            L.mapRes = m.res7;
-            L.mapA0 = m.h_in;
-            L.mapB0 = m.w2;
-            L.mapA1 = proj ? m.xg_in : m.h_in;
-            L.mapB1 = proj ? m.wr : m.w2;
-            L.mapOut = m.u_out7[i & 1];
-            L.bias = bp->bias_t[i];
+            q.wrows = tw::kFramesTile + 2 * q.dmax;
+            q.ttiles = cdiv(T, tw::kFramesTile);
+            q.nboxes = C / 64;
+            q.nq_items = B * q.ttiles;
+            q.bias = bp->bias_t[i];
+            q.PT = ctx->PT;
+            q.PVpart = ctx->PVpart;
+            q.trace = tr ? tr + trn : nullptr;
             L.flops = 2.0 * rows * (3.0 * cr * C + (proj ? (double)cin * C : 0.0));
             L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
-            if ((rc = tc::launch(ctx, K_B_TCONV, L, st))) return rc;
+            if ((rc = tw::launch(ctx, K_B_TCONV, L, st))) return rc;
         }
-        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, gcn::kFramesPerTile))) return rc;
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, tw::kFramesTile))) return rc;
         Uprev = U;
     }
     ctx->cur_block = GS_MAX_BLOCKS;

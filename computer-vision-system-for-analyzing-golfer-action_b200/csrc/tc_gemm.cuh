@@ -64,6 +64,8 @@ struct Program {
     int tile_rows;      // output rows per tile: 128, or 119 (7 whole frames) when stats are taken
     int stats;          // 1: write PT[b,t,n] (sum over joints) and PVpart[b,tile,v,n] (sum over the tile's frames)
     int T;              // frames per clip (stats)
+    int out_joint_major; // 1: mapOut is the 4-D (C, V, T, B) view of a joint-major [B,V,T,C] tensor and a tile is
+                        //    7 whole frames (tile_rows = 119): the store transposes (frame, joint) rows for free
     unsigned long long *trace;   // optional clock64 trace of CTA 0: [5 roles][kTraceTiles][kTraceEv] (tools/trace_tc.py)
     int a_bytes;        // bytes of one A box
     int b_bytes[2];     // bytes of one B box per B map
@@ -152,6 +154,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *s
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -476,7 +484,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
                 if (leader) {
                     TC_TRACE(3 + g, it >> 1, 3 + 4 * q);
-                    tma_store_3d(&mapOut, box, q * 64, row0, b);
+                    if (prog.out_joint_major) tma_store_4d(&mapOut, box, q * 64, 0, mt * 7, b);
+                    else tma_store_3d(&mapOut, box, q * 64, row0, b);
                     tma_store_commit();
                     if (!prog.has_residual) {
                         if (ES == 1) tma_store_wait_read0();   // published to the group by the next box's barrier
@@ -679,23 +688,33 @@ inline bool plan_smem(Program &p, bool allow_resident = true) {
         p.bar_off = p.out_off + 2u * (uint32_t)es * 16384u;
         p.smem_total = p.bar_off + bars + slack;
     };
-    const int es_hi = 2, es_lo = (p.stats || p.has_residual) ? 2 : 1;
-    // preference: resident weights with a deep A ring; give up staging depth before ring depth
-    if (allow_resident) {
-        for (int want : {4, 3})
-            for (int es = es_hi; es >= es_lo; --es)
-                for (int st = kMaxStages; st >= want; --st)
-                    if (wtotal + a_span * st + 2u * es * 16384u + bars + slack <= limit) {
-                        fill(1, st, es);
-                        return true;
-                    }
-    }
-    for (int es = es_hi; es >= es_lo; --es)
-        for (int st = kMaxStages; st >= 2; --st)
+    const int es_lo = (p.stats || p.has_residual) ? 2 : 1;
+    auto try_resident = [&](int es, int min_st) {
+        for (int st = kMaxStages; st >= min_st; --st)
+            if (wtotal + a_span * st + 2u * es * 16384u + bars + slack <= limit) {
+                fill(1, st, es);
+                return true;
+            }
+        return false;
+    };
+    auto try_stream = [&](int es, int min_st) {
+        for (int st = kMaxStages; st >= min_st; --st)
             if ((a_span + bmax) * st + 2u * es * 16384u + bars + slack <= limit) {
                 fill(0, st, es);
                 return true;
             }
+        return false;
+    };
+    // preference: two staging slots per group (the store of box n drains behind box n+1) with resident
+    // weights and a deep A ring; then the same with streamed weights; only then a single slot
+    if (allow_resident && try_resident(2, 4)) return true;
+    if (try_stream(2, 3)) return true;
+    if (allow_resident && try_resident(2, 3)) return true;
+    if (es_lo == 1) {
+        if (allow_resident && try_resident(1, 3)) return true;
+        if (try_stream(1, 2)) return true;
+    }
+    if (try_stream(2, 2)) return true;
     return false;
 }
 
