@@ -149,7 +149,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     uint64_t *acc_empty = d1_full + 8;                // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_full + 10);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int Cin = prm.Cin, C = prm.C;
     const int nbc = Cin / 64;       // 64-channel boxes of the input tile
     const int nq = 3 * nbc;         // XA chunks (= K chunks of the channel mix) per tile

@@ -93,25 +93,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a pipeline bug traps (a reported CUDA error) instead of hanging the GPU.
+// Wait for the phase with the given parity.  The retry loop lives INSIDE one asm statement (as in
+// CUTLASS's ClusterBarrier::wait): a C++ loop on the per-thread try_wait predicate makes the compiler
+// treat everything after it as potentially divergent, which pushes the MMA / TMA operands into vector
+// registers and costs an R2UR round trip per tcgen05.mma (~200-290 cycles each, measured).
+// mbarrier.try_wait suspends in hardware; a pipeline bug shows up as a hang caught by the caller's timeout.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
-    printf("tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-    __trap();
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
+// Warp index as a value the compiler knows is warp-uniform (CUTLASS canonical_warp_idx_sync): role
+// branches on it are uniform branches, so operands of the single-thread instructions stay in uniform
+// registers.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 // One lane of a fully active warp.  The single-thread instructions (tcgen05.mma / commit, TMA) are
 // issued under this predicate from WARP-UNIFORM control flow: measured with experiments/mma_probe.cu,
 // the same tcgen05.mma costs ~175 cycles per issue from a `lane == 0` divergent branch (operands
@@ -258,7 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_empty + 4);
     float *sbias = reinterpret_cast<float *>(smem + prog.bar_off + 512);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
     const int N = prog.N;
     const uint32_t tmem_cols = (2 * N <= 128) ? 128u : (2 * N <= 256 ? 256u : 512u);

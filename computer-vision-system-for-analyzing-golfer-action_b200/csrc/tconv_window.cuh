@@ -46,7 +46,7 @@ struct Params {
     int dil[GS_MAX_BRANCHES];
     int dmax, wrows;  // window rows = 128 + 2*dmax
     int ttiles, nboxes, nq_items;   // frame tiles per clip, 64-channel boxes, items per box (B * ttiles)
-    int stages;
+    int stages, eslots;   // A ring depth; staging slots per epilogue group (2 or 3)
     uint32_t a_span, xg_off, stage_bytes, w_off, wr_off, w_bytes, wr_bytes, out_off, scr_off, bar_off, total;
     const float *bias;    // [C]  (b2 + folded projection bias)
     float *PT;            // [B,T,C]
@@ -87,13 +87,13 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
     uint64_t *tfull = empty + kTwMaxStages;      // [4 accumulator buffers]
     uint64_t *tempty = tfull + 4;
     uint64_t *wres = tempty + 4;
-    uint64_t *res_full = wres + 1;               // [2 groups][2 slots]
-    uint64_t *res_empty = res_full + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_empty + 4);
+    uint64_t *res_full = wres + 1;               // [2 groups][3 slots]
+    uint64_t *res_empty = res_full + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_empty + 6);
     float *sbias = reinterpret_cast<float *>(smem + prm.bar_off + 512);    // [64] (barriers + TMEM slot use < 512 B)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int STAGES = prm.stages;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+    const int STAGES = prm.stages, ES = prm.eslots;
     const int q = blockIdx.x % prm.nboxes;            // this CTA's 64-channel box
     const int cta_in_box = blockIdx.x / prm.nboxes;
     const int ctas_per_box = gridDim.x / prm.nboxes;
@@ -115,6 +115,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         for (int s = 0; s < 4; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], kTwGroup);
+        }
+        for (int s = 0; s < 6; ++s) {
             mbar_init(&res_full[s], 1);
             mbar_init(&res_empty[s], 1);
         }
@@ -157,6 +159,7 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = smem + (size_t)stage * prm.stage_bytes;
                     if (elect_one()) {
+                        TW_TRACE(0, v < 8 ? v : 7, g);
                         mbar_expect_tx(&full[stage], tx);
                         tma_load_4d(sa, &maps.h_win, &full[stage], q * 64, t0 - prm.dmax, v, b);
                         for (int kx = 0; kx < (prm.proj ? prm.nkx : 0); ++kx)
@@ -176,6 +179,20 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         const int ksteps = cr / 16;
         const uint32_t idesc_tap = make_idesc_bf16((uint32_t)cr);
         const uint32_t idesc_proj = make_idesc_bf16(64u);
+        // Everything that does not depend on the stage is computed ONCE: per (branch, tap) the byte offset of
+        // the A start row inside the window and the weight descriptor; per step an MMA costs one 64-bit add.
+        // (Descriptors rebuilt next to every tcgen05.mma cost ~200 cycles each through the uniform datapath.)
+        uint32_t aoff[12], dcol[12];
+        uint64_t dbv[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int rl = i / 3, j = i % 3;
+            const int d = rl < prm.nbr ? prm.dil[q * prm.nbr + rl] : 0;
+            aoff[i] = ((uint32_t)(prm.dmax + (j - 1) * d) * 128u + (uint32_t)(rl * cr * 2)) >> 4;
+            dcol[i] = (uint32_t)(rl * cr);
+            dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w_off + (size_t)i * (cr * cr * 2)), wrow_bytes);
+        }
+        const int ntap = 3 * prm.nbr;
         mbar_wait(wres, 0);
         for (int i0 = first_item; i0 < prm.nq_items; i0 += item_stride) {
             for (int v = 0; v < 17; ++v) {
@@ -184,13 +201,16 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                     if (i0 + g * ctas_per_box >= prm.nq_items) continue;
                     const uint32_t n = ng[g];
                     const uint32_t buf = 2u * (n & 1u) + (uint32_t)g;
+                    if (lane == 0) TW_TRACE(1, (int)n, 6 + g);
                     mbar_wait(&tempty[buf], ((n >> 1) & 1u) ^ 1u);
+                    if (lane == 0) TW_TRACE(1, (int)n, 2 + g);
                     mbar_wait(&full[stage], phase);
+                    if (lane == 0) TW_TRACE(1, (int)n, 4 + g);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
                     const uint32_t td = tmem_base + buf * 64u;
+                    const uint64_t da0 = make_kmajor_desc(sa, 128);
                     if (elect_one()) {
-                        TW_TRACE(1, (int)n, g);
                         if (prm.proj) {
                             for (int kx = 0; kx < prm.nkx; ++kx) {
                                 const uint64_t da = make_kmajor_desc(sa + prm.xg_off + (uint32_t)kx * 16384u, 128);
@@ -201,19 +221,17 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                                               (uint32_t)((kx > 0) | (k > 0)));
                             }
                         }
-                        for (int rl = 0; rl < prm.nbr; ++rl) {
-                            const int d = prm.dil[q * prm.nbr + rl];
-                            for (int j = 0; j < 3; ++j) {
-                                // A: rows (dmax + (j-1)d ..+128) of the window, K offset rl*cr inside the 128 B row
-                                const uint64_t da = make_kmajor_desc(
-                                    sa + (uint32_t)(prm.dmax + (j - 1) * d) * 128u + (uint32_t)(rl * cr * 2), 128);
-                                const uint64_t db =
-                                    make_kmajor_desc(smem_u32(smem + prm.w_off + (size_t)(rl * 3 + j) * (cr * cr * 2)), wrow_bytes);
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) {
+                            if (i < ntap) {
+                                const uint64_t da = da0 + (uint64_t)aoff[i];
+                                const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0));
                                 for (int k = 0; k < ksteps; ++k)
-                                    umma_bf16(td + (uint32_t)(rl * cr), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tap,
-                                              (uint32_t)(prm.proj | (j > 0) | (k > 0)));
+                                    umma_bf16(td + dcol[i], da + (uint64_t)(2 * k), dbv[i] + (uint64_t)(2 * k), idesc_tap,
+                                              accum | (uint32_t)(k > 0));
                             }
                         }
+                        TW_TRACE(1, (int)n, g);
                         umma_commit(&empty[stage]);
                         umma_commit(&tfull[buf]);
                     }
@@ -232,12 +250,12 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
             for (int i0 = first_item + g * ctas_per_box; i0 < prm.nq_items; i0 += item_stride) {
                 const int b = i0 / prm.ttiles, t0 = (i0 % prm.ttiles) * kFramesTile;
                 for (int v = 0; v < 17; ++v) {
-                    const uint32_t sl = ecnt & 1u, ph = (ecnt >> 1) & 1u;
-                    uint64_t *rf = &res_full[g * 2 + (int)sl];
-                    mbar_wait(&res_empty[g * 2 + (int)sl], ph ^ 1u);
+                    const uint32_t sl = ecnt % (uint32_t)ES, ph = (ecnt / (uint32_t)ES) & 1u;
+                    uint64_t *rf = &res_full[g * 3 + (int)sl];
+                    mbar_wait(&res_empty[g * 3 + (int)sl], ph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(rf, 16384u);
-                        tma_load_4d(smem + prm.out_off + (size_t)(g * 2 + (int)sl) * 16384, &maps.res, rf, q * 64, v, t0, b);
+                        tma_load_4d(smem + prm.out_off + (size_t)(g * ES + (int)sl) * 16384, &maps.res, rf, q * 64, v, t0, b);
                     }
                     __syncwarp();
                     ++ecnt;
@@ -253,7 +271,7 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         const int r = ew * 32 + lane;                        // frame inside the tile
         const bool leader = (gt == 0);
         const int bar_id = 1 + g;
-        unsigned char *sout = smem + prm.out_off + (size_t)(g * 2) * 16384;
+        unsigned char *sout = smem + prm.out_off + (size_t)(g * ES) * 16384;
         float *scr = reinterpret_cast<float *>(smem + prm.scr_off) + g * (2 * 8 * 64);    // [2][8 parts][64]
         const int c2 = gt & 31, part = gt >> 5;              // pooling: channel pair, row part (16 rows each)
         uint32_t n = 0;                                      // steps done by this group
@@ -282,13 +300,15 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
             for (int e = 0; e < 32; ++e) pt[e] = 0.f;
             for (int v = 0; v < 17; ++v, ++n) {
                 const uint32_t buf = 2u * (n & 1u) + (uint32_t)g;
-                const uint32_t es = n & 1u, eph = (n >> 1) & 1u;
+                const uint32_t es = n % (uint32_t)ES, eph = (n / (uint32_t)ES) & 1u;
                 unsigned char *box = sout + (size_t)es * 16384;
+                if (leader) TW_TRACE(3 + g, (int)n, 5);
                 mbar_wait(&tfull[buf], (n >> 1) & 1u);
+                if (leader) TW_TRACE(3 + g, (int)n, 6);
                 tc_fence_after();
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 64u + (uint32_t)(half * 32), acc);
-                if (!prm.proj) mbar_wait(&res_full[g * 2 + (int)es], eph);   // slot is ours and holds the residual box
+                if (!prm.proj) mbar_wait(&res_full[g * 3 + (int)es], eph);   // slot is ours and holds the residual box
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tempty[buf]);
@@ -333,14 +353,16 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                 // projection blocks have no slot producer: the store issued a step ago (the only one pending)
                 // must have read its slot before the NEXT step overwrites it; that step starts after this barrier
                 if (leader && prm.proj) tma_store_wait_read0();
+                if (leader) TW_TRACE(3 + g, (int)n, 1);
                 asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
                 if (leader) {
+                    TW_TRACE(3 + g, (int)n, 2);
                     tma_store_4d(&maps.out, box, q * 64, v, t0, b);
                     tma_store_commit();
                     if (!prm.proj) {
                         if (pending >= 0) {
                             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            mbar_arrive(&res_empty[g * 2 + pending]);
+                            mbar_arrive(&res_empty[g * 3 + pending]);
                         }
                         pending = (int)es;
                     }
@@ -367,6 +389,7 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                         }
                     *reinterpret_cast<float2 *>(scr + (n & 1u) * (8 * 64) + part * 64 + 2 * c2) = a2;
                 }
+                if (leader) TW_TRACE(3 + g, (int)n, 3);
                 fin_b = b;
                 fin_tt = tt;
                 fin_v = v;
@@ -457,17 +480,23 @@ inline bool plan(Params &p) {
     p.w_bytes = (uint32_t)(p.nbr * 3 * p.cr * p.cr * 2);
     p.wr_bytes = p.proj ? (uint32_t)p.nkx * 8192u : 0u;
     const uint32_t wspan = ((p.w_bytes + 1023u) & ~1023u) + p.wr_bytes;
-    const uint32_t fixed = wspan + 4u * 16384u + 8192u /*pooling scratch: 2 groups x [2][8][64] floats*/ + 1024u /*barriers + bias*/ + 1024u /*slack*/;
-    for (int st = kTwMaxStages; st >= 2; --st) {
-        if (p.stage_bytes * st + fixed <= limit) {
-            p.stages = st;
-            p.w_off = p.stage_bytes * st;
-            p.wr_off = p.w_off + ((p.w_bytes + 1023u) & ~1023u);
-            p.out_off = p.w_off + wspan;
-            p.scr_off = p.out_off + 4u * 16384u;
-            p.bar_off = p.scr_off + 8192u;
-            p.total = p.bar_off + 1024u + 1024u;
-            return true;
+    // three staging slots per group give the residual box two steps of lookahead (its TMA latency is about
+    // one step); projection blocks have no residual box and stay with two
+    for (int es = p.proj ? 2 : 3; es >= 2; --es) {
+        const uint32_t fixed = wspan + 2u * es * 16384u + 8192u /*pooling scratch: 2 groups x [2][8][64] floats*/ +
+                               1024u /*barriers + bias*/ + 1024u /*slack*/;
+        for (int st = kTwMaxStages; st >= (es == 3 ? 4 : 2); --st) {
+            if (p.stage_bytes * st + fixed <= limit) {
+                p.stages = st;
+                p.eslots = es;
+                p.w_off = p.stage_bytes * st;
+                p.wr_off = p.w_off + ((p.w_bytes + 1023u) & ~1023u);
+                p.out_off = p.w_off + wspan;
+                p.scr_off = p.out_off + 2u * es * 16384u;
+                p.bar_off = p.scr_off + 8192u;
+                p.total = p.bar_off + 1024u + 1024u;
+                return true;
+            }
         }
     }
     return false;

@@ -31,6 +31,18 @@ for blk in blocks:
         nq = C // 64
         print(f"=== block {blk} {kname} (C={C}); cycles relative to first event")
         rel = lambda a: [int(v - t0) if v > 0 else -1 for v in a]
+        if kname == "tconv":
+            # tconv_window.cuh roles: 0 producer [v][g], 1 mma [n][g], 3+g epilogue [n]: 5 wait acc, 6 acc ready,
+            # 0 TMEM loaded, 1 staged, 2 barrier passed, 3 pooling done
+            for n in range(8):
+                print(f" step {n}: mma g0: top {rel(t[1, n, 6:7])} acc-free {rel(t[1, n, 2:3])} data {rel(t[1, n, 4:5])} issued {rel(t[1, n, 0:1])}"
+                      f" | g1: top {rel(t[1, n, 7:8])} acc-free {rel(t[1, n, 3:4])} data {rel(t[1, n, 5:6])} issued {rel(t[1, n, 1:2])}")
+            for g in (0, 1):
+                for n in range(8):
+                    e = t[3 + g, n]
+                    print(f"   group {g} step {n}: wait {rel(e[5:6])} acc {rel(e[6:7])} ld {rel(e[0:1])} staged {rel(e[1:2])} "
+                          f"bar {rel(e[2:3])} pooled {rel(e[3:4])}")
+            continue
         for tile in range(1, 5):
             nz = int((t[0, tile] > 0).sum())
             print(f" tile {tile}: prod {rel(t[0, tile, :nz])}")
