@@ -78,6 +78,9 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// CR = channels per branch (16 / 32 / 64): compile-time so the tap loop of the MMA issuer is straight-line
+// code (12 tcgen05.mma per step with loop-invariant operand offsets).
+template <int CR>
 __global__ void __launch_bounds__(kTwThreads, 1)
 tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params prm) {
     extern __shared__ unsigned char smem_raw[];
@@ -97,7 +100,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
     const int q = blockIdx.x % prm.nboxes;            // this CTA's 64-channel box
     const int cta_in_box = blockIdx.x / prm.nboxes;
     const int ctas_per_box = gridDim.x / prm.nboxes;
-    const int T = prm.T, cr = prm.cr;
+    const int T = prm.T;
+    constexpr int cr = CR, NBR = 64 / CR;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.h_win);
@@ -139,10 +143,10 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         // ===== producer: one stage per step = H window of (joint v, box q) [+ projection-input boxes] =====
         if (elect_one()) {
             mbar_expect_tx(wres, prm.w_bytes + prm.wr_bytes);
-            for (int rl = 0; rl < prm.nbr; ++rl)
+            for (int rl = 0; rl < NBR; ++rl)
                 for (int j = 0; j < 3; ++j)
                     tma_load_2d(smem + prm.w_off + (size_t)(rl * 3 + j) * (cr * cr * 2), &maps.w2, wres, 0,
-                                ((q * prm.nbr + rl) * 3 + j) * cr);
+                                ((q * NBR + rl) * 3 + j) * cr);
             for (int kx = 0; kx < (prm.proj ? prm.nkx : 0); ++kx)
                 tma_load_2d(smem + prm.wr_off + (size_t)kx * 8192, &maps.wr, wres, kx * 64, q * 64);
         }
@@ -175,8 +179,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         int stage = 0;
         uint32_t phase = 0;
         uint32_t ng[2] = {0, 0};                 // steps issued per group
-        const uint32_t wrow_bytes = (uint32_t)cr * 2;
-        const int ksteps = cr / 16;
+        constexpr uint32_t wrow_bytes = (uint32_t)CR * 2;
+        constexpr int ksteps = CR / 16;
         const uint32_t idesc_tap = make_idesc_bf16((uint32_t)cr);
         const uint32_t idesc_proj = make_idesc_bf16(64u);
         // Everything that does not depend on the stage is computed ONCE: per (branch, tap) the byte offset of
@@ -187,12 +191,12 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
             const int rl = i / 3, j = i % 3;
-            const int d = rl < prm.nbr ? prm.dil[q * prm.nbr + rl] : 0;
+            const int d = rl < NBR ? prm.dil[q * NBR + rl] : 0;
             aoff[i] = ((uint32_t)(prm.dmax + (j - 1) * d) * 128u + (uint32_t)(rl * cr * 2)) >> 4;
             dcol[i] = (uint32_t)(rl * cr);
             dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w_off + (size_t)i * (cr * cr * 2)), wrow_bytes);
         }
-        const int ntap = 3 * prm.nbr;
+        constexpr int ntap = 3 * NBR;
         mbar_wait(wres, 0);
         for (int i0 = first_item; i0 < prm.nq_items; i0 += item_stride) {
             for (int v = 0; v < 17; ++v) {
@@ -210,27 +214,35 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                     const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
                     const uint32_t td = tmem_base + buf * 64u;
                     const uint64_t da0 = make_kmajor_desc(sa, 128);
+                    // operands are warp-uniform values computed in uniform code; only the tcgen05 instruction itself
+                    // sits under the elected lane (operands produced inside the elected branch live in vector
+                    // registers and cost an R2UR round trip per MMA: 237 cycles each, measured)
+                    if (prm.proj) {
+                        for (int kx = 0; kx < prm.nkx; ++kx) {
+                            const uint64_t da = make_kmajor_desc(sa + prm.xg_off + (uint32_t)kx * 16384u, 128);
+                            const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.wr_off + (size_t)kx * 8192), 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t accum = (uint32_t)((kx > 0) | (k > 0));
+                                if (elect_one()) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_proj, accum);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        if (i < ntap) {
+                            const uint64_t da = da0 + (uint64_t)aoff[i];
+                            const uint64_t db = dbv[i];
+                            const uint32_t tdr = td + dcol[i];
+                            const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0));
+#pragma unroll
+                            for (int k = 0; k < ksteps; ++k) {
+                                const uint32_t acc_k = accum | (uint32_t)(k > 0);
+                                if (elect_one()) umma_bf16(tdr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tap, acc_k);
+                            }
+                        }
+                    }
                     if (elect_one()) {
-                        if (prm.proj) {
-                            for (int kx = 0; kx < prm.nkx; ++kx) {
-                                const uint64_t da = make_kmajor_desc(sa + prm.xg_off + (uint32_t)kx * 16384u, 128);
-                                const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.wr_off + (size_t)kx * 8192), 128);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_proj,
-                                              (uint32_t)((kx > 0) | (k > 0)));
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) {
-                            if (i < ntap) {
-                                const uint64_t da = da0 + (uint64_t)aoff[i];
-                                const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0));
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_bf16(td + dcol[i], da + (uint64_t)(2 * k), dbv[i] + (uint64_t)(2 * k), idesc_tap,
-                                              accum | (uint32_t)(k > 0));
-                            }
-                        }
                         TW_TRACE(1, (int)n, g);
                         umma_commit(&empty[stage]);
                         umma_commit(&tfull[buf]);
@@ -517,10 +529,11 @@ inline int launch(Ctx *ctx, int kid, LaunchTw &L, cudaStream_t st) {
     const int need = L.prm.nq_items * L.prm.nboxes;
     if (grid > need) grid = need;
     if (grid < 1) return GS_OK;
-    GS_CUDA(cudaFuncSetAttribute(tconv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.prm.total));
+    auto kern = L.prm.cr == 16 ? tconv_window_kernel<16> : (L.prm.cr == 32 ? tconv_window_kernel<32> : tconv_window_kernel<64>);
+    GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.prm.total));
     {
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
-        tconv_window_kernel<<<grid, kTwThreads, L.prm.total, st>>>(L.maps, L.prm);
+        kern<<<grid, kTwThreads, L.prm.total, st>>>(L.maps, L.prm);
     }
     GS_KERNEL_CHECK();
     return GS_OK;

@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps, in
         tc_fence_after();
     }
     // two / four issuing warps at once (different accumulators): is the limit per issuing warp or per SM?
-    for (int test = 0; test < 7; ++test) {
+    for (int test = 0; test < 12; ++test) {
         const int nw = test == 0 ? 2 : (test >= 3 ? 1 : 4);                 // warps 0..nw-1 issue
-        const uint32_t n = test == 2 ? 16u : (test == 4 ? 256u : (test == 5 ? 128u : (test == 6 ? 16u : 64u)));
+        const uint32_t n = test == 2 ? 16u : (test == 4 ? 256u : (test == 5 ? 128u : ((test == 6 || test >= 9) ? 16u : 64u)));
+        // tests 7..11: A start row offset inside a SW128 tile and B layout, as the sliding-window conv uses them
+        const uint32_t arow = (test == 7 || test == 10) ? 1u : (test == 8 || test == 11 ? 8u : 0u);
+        const bool b_sw32 = test >= 9;
         __shared__ uint64_t bars2[4];
         if (threadIdx.x == 0) {
             for (int i = 0; i < 4; ++i) mbar_init(&bars2[i], 1);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Result *out, int reps, in
         __syncthreads();
         if (warp < nw) {
             const uint32_t a = smem_u32(sA), b = smem_u32(sB);
-            const uint64_t da = make_kmajor_desc(a, 128), db = make_kmajor_desc(b, 128);
+            const uint64_t da = make_kmajor_desc(a + arow * 128u, 128), db = make_kmajor_desc(b, b_sw32 ? 32 : 128);
             const uint32_t id = make_idesc_bf16(n);
             __syncwarp();
             const long long t0 = clock64();
@@ -319,15 +322,17 @@ int main(int argc, char **argv) {
     }
     Result h;
     cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    const char *names[26] = {"SS K/K  N=256", "SS K/K  N=128", "SS K/K  N=64", "SS K/K  N=16 (SW32)", "TS A=tmem, B MN-major N=64",
+    const char *names[31] = {"SS K/K  N=256", "SS K/K  N=128", "SS K/K  N=64", "SS K/K  N=16 (SW32)", "TS A=tmem, B MN-major N=64",
                              "TS A=tmem, B K-major N=64", "TS A=tmem, B K-major N=256", "SS A K-major, B MN-major N=64",
                              "SS K/K  N=32", "tcgen05.ld 32x32b.x32 + wait", "mbar_wait (already complete)",
                              "elect: SS K/K N=256", "elect: SS K/K N=64", "elect: TS B MN-major N=64", "elect: TS B K-major N=256",
                              "elect: SS N=64, 2 accumulators", "elect: SS N=64, 4 accumulators", "elect: SS N=256, 2 accumulators",
                              "elect: SS N=16, 8 accumulators", "2 issuing warps N=64 (per MMA)", "4 issuing warps N=64 (per MMA)",
                              "4 issuing warps N=16 (per MMA)", "1 warp clean loop N=64", "1 warp clean loop N=256",
-                             "1 warp clean loop N=128", "1 warp clean loop N=16"};
-    for (int t = 0; t < 26; ++t)
+                             "1 warp clean loop N=128", "1 warp clean loop N=16",
+                             "clean N=64, A start +1 row", "clean N=64, A start +8 rows", "clean N=16 A SW128 B SW32",
+                             "clean N=16 A +1 row, B SW32", "clean N=16 A +8 rows, B SW32"};
+    for (int t = 0; t < 31; ++t)
         printf("%-34s issue %8.1f cyc/op   total %8.1f cyc/op   (reps %lld)\n", names[t],
                (double)h.cyc[t][0] / h.cyc[t][2], (double)h.cyc[t][1] / h.cyc[t][2], h.cyc[t][2]);
     const int shifts[8] = {0, 8, 1, 3, 17, 34, 51, 68};
