@@ -31,8 +31,10 @@ struct BlockMaps {
 struct Bf16Path {
     std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
     std::vector<float *> bias_t;                        // b2 (+ br)
+    std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in TF32 fragment order (stj_tc_kernel)
     std::vector<BlockMaps> maps;
     int maps_T = -1;
+    bool stj_tc = true;         // GOLFER_STJ_FFMA=1 keeps the exact-fp32 FFMA ST-joint kernel
     bool fused_gcn = true;      // GOLFER_GCN_UNFUSED=1 selects the SIMT-aggregate + dense-GEMM pair
     bool debug_xa = false;      // GOLFER_DEBUG_XA=1 dumps the fused kernel's XA chunks into bufXA
     unsigned long long *trace = nullptr;   // GOLFER_TRACE_GCN=1: [blocks][5 roles][6 tiles][64 events] clock64
@@ -283,27 +285,14 @@ int bf16_path_create(Ctx *ctx) {
     Bf16Path *bp = new Bf16Path();
     ctx->bf16 = bp;
     if (const char *e = getenv("GOLFER_GCN_UNFUSED")) bp->fused_gcn = !(e[0] == '1');
-    if (const char *e = getenv("GOLFER_DEBUG_XA")) bp->debug_xa = (e[0] == '1');
-    if (const char *e = getenv("GOLFER_TRACE_GCN")) {
-        if (e[0] == '1') {
-            const size_t n = (size_t)GS_MAX_BLOCKS * 5 * gcn::kTraceTiles * gcn::kTraceEv;
-            GS_CUDA(cudaMalloc((void **)&bp->trace, n * 8));
-            GS_CUDA(cudaMemset(bp->trace, 0, n * 8));
-        }
-    }
-    if (const char *e = getenv("GOLFER_TRACE_TC")) {
-        if (e[0] == '1') {
-            const size_t n = (size_t)GS_MAX_BLOCKS * 2 * 5 * tc::kTraceTiles * tc::kTraceEv;
-            GS_CUDA(cudaMalloc((void **)&bp->trace_tc, n * 8));
-            GS_CUDA(cudaMemset(bp->trace_tc, 0, n * 8));
-        }
-    }
+    if (const char *e = getenv("GOLFER_STJ_FFMA")) bp->stj_tc = !(e[0] == '1');
     const size_t nb = ctx->blocks.size();
     bp->WgT.assign(nb, nullptr);
     bp->W1T.assign(nb, nullptr);
     bp->W2p.assign(nb, nullptr);
     bp->WrT.assign(nb, nullptr);
     bp->bias_t.assign(nb, nullptr);
+    for (auto &v : bp->stjP) v.assign(nb, nullptr);
     const float *hb = ctx->h_blob.data();
     auto host = [&](const float *dev_ptr) { return hb + (dev_ptr - ctx->d_blob); };
     int rc;
@@ -345,6 +334,24 @@ int bf16_path_create(Ctx *ctx) {
             const float *brh = host(b.br);
             for (int n = 0; n < C; ++n) bias[n] += brh[n];
         }
+        if (bp->stj_tc && C == 4 * b.cj && (C == 64 || C == 128 || C == 256)) {
+            const int Q = C / 64;
+            const float *srcs[3] = {host(b.jW), host(b.jWt), host(b.jWv)};
+            for (int w = 0; w < 3; ++w) {
+                std::vector<float> packed;
+                if (w == 0) pack_stj_fragments(srcs[w], C, b.cj, Q, 1, packed);
+                else pack_stj_fragments(srcs[w], b.cj, C, Q == 1 ? 4 : 8, Q == 4 ? 2 : 1, packed);
+                for (float &x : packed) {      // round to nearest TF32 (10 explicit mantissa bits)
+                    uint32_t u;
+                    memcpy(&u, &x, 4);
+                    u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+                    memcpy(&x, &u, 4);
+                }
+                GS_CUDA(cudaMalloc((void **)&bp->stjP[w][i], packed.size() * sizeof(float)));
+                ctx->ws_bytes += packed.size() * sizeof(float);
+                GS_CUDA(cudaMemcpy(bp->stjP[w][i], packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        }
         GS_CUDA(cudaMalloc((void **)&bp->bias_t[i], C * sizeof(float)));
         GS_CUDA(cudaMemcpy(bp->bias_t[i], bias.data(), C * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -359,6 +366,9 @@ void bf16_path_destroy(Ctx *ctx) {
             if (p) cudaFree(p);
     for (float *p : bp->bias_t)
         if (p) cudaFree(p);
+    for (auto &v : bp->stjP)
+        for (float *p : v)
+            if (p) cudaFree(p);
     if (bp->trace) cudaFree(bp->trace);
     if (bp->trace_tc) cudaFree(bp->trace_tc);
     delete bp;
@@ -479,7 +489,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
             if ((rc = tw::launch(ctx, K_B_TCONV, L, st))) return rc;
         }
-        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, tw::kFramesTile))) return rc;
+        const float *stjp[3] = {bp->stjP[0][i], bp->stjP[1][i], bp->stjP[2][i]};
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, tw::kFramesTile, stjp[0] ? stjp : nullptr))) return rc;
         Uprev = U;
     }
     ctx->cur_block = GS_MAX_BLOCKS;

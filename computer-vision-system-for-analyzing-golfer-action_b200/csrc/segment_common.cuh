@@ -272,6 +272,169 @@ stj_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const flo
     }
 }
 
+// ---- ST-joint attention on warp-level tensor cores (bf16 path) ----------------------------------
+// Same math as stj_kernel with both small GEMMs as mma.sync m16n8k8 TF32 (fp32 accumulate): the FFMA
+// form is bound at ~70 us per C=256 launch by FMA issue alone.  One CTA = 64 positions of one clip;
+// 8 warps = 4 (16-row slabs) x 2 (column halves).  The three weight matrices are rounded to TF32 and
+// re-packed once at context creation, pooled / hidden activations are rounded when they are staged.
+// The fp32 parity path keeps stj_kernel (exact fp32).
+constexpr int kStjTcPos = 64;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Q = cj / 16 with C = 64 * Q (ST-joint reduction 4).  Weights arrive re-packed in FRAGMENT ORDER
+// (host: pack_stj_fragments): for every k-step, column half and lane the B-fragment registers of all its
+// n-tiles are contiguous, so a warp fetches them with one or two 16-byte loads per lane (fully coalesced)
+// instead of 8-16 scalar loads of 32-byte segments.
+template <int V, int Q>
+__global__ void __launch_bounds__(256)
+stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const float *__restrict__ seS, int T,
+              int ntT, const float *__restrict__ P1, const float *__restrict__ bW, const float *__restrict__ P2t,
+              const float *__restrict__ bt, const float *__restrict__ P2v, const float *__restrict__ bv,
+              float *__restrict__ gT, float *__restrict__ gV) {
+    constexpr int C = 64 * Q, cj = 16 * Q;
+    constexpr int NT1 = Q;                       // n-tiles per warp, first GEMM (cj/2 columns)
+    constexpr int NT2 = Q == 1 ? 4 : 8;          // n-tiles per warp and pass, second GEMM
+    constexpr int NPASS = Q == 4 ? 2 : 1;        // passes of 64 columns over this warp's C/2 columns
+    constexpr int ldp = C + 4, lda = cj + 4;     // +4 floats: conflict-free A-fragment loads
+    extern __shared__ __align__(16) float sm[];
+    uint32_t *sp = reinterpret_cast<uint32_t *>(sm);              // pooled [64][ldp] tf32
+    uint32_t *sa = sp + kStjTcPos * ldp;                           // hidden [64][lda] tf32
+    const int b = blockIdx.y;
+    const bool is_t = (int)blockIdx.x < ntT;
+    const int p0 = (is_t ? blockIdx.x : blockIdx.x - ntT) * kStjTcPos;
+    const int np = min(kStjTcPos, (is_t ? T : V) - p0);
+    const float inv = is_t ? 1.0f / (float)V : 1.0f / (float)T;
+    const float *src = is_t ? PT + ((size_t)b * T + p0) * C : PV + ((size_t)b * V + p0) * C;
+    for (int e = threadIdx.x * 4; e < kStjTcPos * C; e += blockDim.x * 4) {
+        const int qq = e / C, c = e - qq * C;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qq < np) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(seS + (size_t)b * C + c));
+            const float4 v4 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)qq * C + c));
+            x = make_float4(s4.x * (v4.x * inv), s4.y * (v4.y * inv), s4.z * (v4.z * inv), s4.w * (v4.w * inv));
+        }
+        *reinterpret_cast<uint4 *>(sp + qq * ldp + c) = make_uint4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 3, wn = warp >> 2, gr = lane >> 2, tg = lane & 3;
+    const int r0 = wm * 16 + gr, r1 = r0 + 8;
+    {   // hidden = hswish(pooled . W + bW): this warp's 16 rows x cj/2 columns
+        constexpr int ncols = cj / 2;
+        const int nb = wn * ncols;
+        float acc[NT1][4];
+#pragma unroll
+        for (int t = 0; t < NT1; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+        const float *pw = P1 + ((size_t)wn * 32 + lane) * (NT1 * 2);
+#pragma unroll 4
+        for (int ks = 0; ks < C / 8; ++ks) {
+            const int k0 = ks * 8;
+            const uint32_t a0 = sp[r0 * ldp + k0 + tg], a1 = sp[r1 * ldp + k0 + tg];
+            const uint32_t a2 = sp[r0 * ldp + k0 + tg + 4], a3 = sp[r1 * ldp + k0 + tg + 4];
+            float bf[NT1 * 2];
+            const float *pk = pw + (size_t)ks * (2 * 32 * NT1 * 2);
+            if constexpr (NT1 == 1) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(pk));
+                bf[0] = v.x; bf[1] = v.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NT1 / 2; ++i) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(pk) + i);
+                    bf[4 * i] = v.x; bf[4 * i + 1] = v.y; bf[4 * i + 2] = v.z; bf[4 * i + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NT1; ++t)
+                mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
+        }
+#pragma unroll
+        for (int t = 0; t < NT1; ++t) {
+            const int col = nb + t * 8 + 2 * tg;
+            const float b0 = bW[col], b1 = bW[col + 1];
+            sa[r0 * lda + col] = to_tf32(hardswishf(acc[t][0] + b0));
+            sa[r0 * lda + col + 1] = to_tf32(hardswishf(acc[t][1] + b1));
+            sa[r1 * lda + col] = to_tf32(hardswishf(acc[t][2] + b0));
+            sa[r1 * lda + col + 1] = to_tf32(hardswishf(acc[t][3] + b1));
+        }
+    }
+    __syncthreads();
+    const float *P2 = is_t ? P2t : P2v;
+    const float *bo = is_t ? bt : bv;
+    float *dst = is_t ? gT + ((size_t)b * T + p0) * C : gV + ((size_t)b * V + p0) * C;
+    constexpr int ncols2 = C / 2;
+    const int nb2 = wn * ncols2;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        float acc[NT2][4];
+#pragma unroll
+        for (int t = 0; t < NT2; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < cj / 8; ++ks) {
+            const int k0 = ks * 8;
+            const uint32_t a0 = sa[r0 * lda + k0 + tg], a1 = sa[r1 * lda + k0 + tg];
+            const uint32_t a2 = sa[r0 * lda + k0 + tg + 4], a3 = sa[r1 * lda + k0 + tg + 4];
+            const float4 *pk = reinterpret_cast<const float4 *>(
+                P2 + ((((size_t)ks * 2 + wn) * NPASS + pass) * 32 + lane) * (NT2 * 2));
+            float bf[NT2 * 2];
+#pragma unroll
+            for (int i = 0; i < NT2 / 2; ++i) {
+                const float4 v = __ldg(pk + i);
+                bf[4 * i] = v.x; bf[4 * i + 1] = v.y; bf[4 * i + 2] = v.z; bf[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int t = 0; t < NT2; ++t)
+                mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
+        }
+#pragma unroll
+        for (int t = 0; t < NT2; ++t) {
+            const int col = nb2 + pass * 64 + t * 8 + 2 * tg;
+            const float2 bc = *reinterpret_cast<const float2 *>(bo + col);
+            float2 s2 = make_float2(1.f, 1.f);
+            if (is_t) s2 = *reinterpret_cast<const float2 *>(seS + (size_t)b * C + col);
+            if (r0 < np)
+                *reinterpret_cast<float2 *>(dst + (size_t)r0 * C + col) =
+                    make_float2(s2.x * sigmoidf_acc(acc[t][0] + bc.x), s2.y * sigmoidf_acc(acc[t][1] + bc.y));
+            if (r1 < np)
+                *reinterpret_cast<float2 *>(dst + (size_t)r1 * C + col) =
+                    make_float2(s2.x * sigmoidf_acc(acc[t][2] + bc.x), s2.y * sigmoidf_acc(acc[t][3] + bc.y));
+        }
+    }
+}
+
+// Host: re-pack W [K][N] (row-major) into mma.sync m16n8k8 B-fragment order for a warp grid of 2 column
+// halves, `nt` n-tiles per warp and pass:  out[ks][wn][pass][lane][t*2 + h] = W[ks*8 + (lane&3) + 4h][col],
+// col = wn*(N/2) + pass*64 + t*8 + (lane>>2).
+inline void pack_stj_fragments(const float *W, int K, int N, int nt, int npass, std::vector<float> &out) {
+    out.assign((size_t)K * N, 0.f);
+    size_t o = 0;
+    for (int ks = 0; ks < K / 8; ++ks)
+        for (int wn = 0; wn < 2; ++wn)
+            for (int pass = 0; pass < npass; ++pass)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int t = 0; t < nt; ++t)
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = ks * 8 + (lane & 3) + 4 * h;
+                            const int col = wn * (N / 2) + pass * 64 + t * 8 + (lane >> 2);
+                            out[o++] = W[(size_t)k * N + col];
+                        }
+}
+
 // ---- head (README.md:17-18) -----------------------------------------------------------
 // logits[b,t,k] = sum_c (gT[b,t,c] * sum_v U[b,t,v,c]*gV[b,v,c] / V) * Wh[c,k] + bh[k]
 // One WARP per frame (8 warps, kHeadFrames frames of one clip per CTA); a lane owns 8-channel
@@ -383,11 +546,12 @@ features_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const fl
 }
 
 // Host-side launcher for the attention tail of one block (stats -> SE -> ST-joint).
+// `stj_packed` (bf16 path): fragment-ordered TF32 copies of {W, Wt, Wv} for stj_tc_kernel.
 // `fused_chunk` > 0: PT / PVpart were already written by the producing kernel's epilogue with
 // chunks of that many frames (tc_gemm.cuh); 0: run stats_kernel here.
 template <typename TU>
 int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T, cudaStream_t st,
-                     int fused_chunk = 0) {
+                     int fused_chunk = 0, const float *const *stj_packed = nullptr) {
     constexpr int V = 17;
     const int C = bp.c;
     const int nchunk = cdiv(T, fused_chunk > 0 ? fused_chunk : kStatChunk);
@@ -409,7 +573,19 @@ int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T,
         }
         GS_KERNEL_CHECK();
     }
-    {
+    if (stj_packed && C == 4 * bp.cj && (C == 64 || C == 128 || C == 256)) {
+        const int ntT = cdiv(T, kStjTcPos);
+        dim3 grid(ntT + cdiv(V, kStjTcPos), B);
+        const size_t smem = (size_t)kStjTcPos * ((C + 4) + (bp.cj + 4)) * sizeof(float);
+        auto kern = C == 64 ? stj_tc_kernel<V, 1> : (C == 128 ? stj_tc_kernel<V, 2> : stj_tc_kernel<V, 4>);
+        if (smem > 48 * 1024) GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            LaunchScope ls(ctx, K_STJ, st, 4.0 * B * (T + V) * C * bp.cj, 2.0 * B * (T + V) * C * 4);
+            kern<<<grid, 256, smem, st>>>(ctx->PT, ctx->PV, ctx->seS, T, ntT, stj_packed[0], bp.jb, stj_packed[1], bp.jbt,
+                                          stj_packed[2], bp.jbv, ctx->gT, ctx->gV);
+        }
+        GS_KERNEL_CHECK();
+    } else {
         const int ntT = cdiv(T, kStjPos);
         dim3 grid(ntT + cdiv(V, kStjPos), B);
         const size_t smem = ((size_t)C * kStjLd + (size_t)bp.cj * kStjPos) * sizeof(float);
