@@ -297,17 +297,24 @@ def main():
                              "ms_per_launch_by_block": {str(bk): round(bv["ms"] / bv["launches"], 4)
                                                         for bk, bv in v.get("blocks", {}).items()}}
         top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        traffic = None      # ncu dram bytes per launch of that kernel (profiles/r1_traffic.json, same workload)
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath) and B == BATCH:
+            traffic = json.load(open(tpath)).get(top, {}).get("bytes_per_launch")
         tensor_bound = "gemm" in top or "tconv" in top
         if tensor_bound:
             ach = tv["flops"] / tv["ms"] / 1e9
             peak = peaks["tf_sust"]
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
+                        "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
                         "peak_source": f"{peaks['source']} bf16 sustained"}
         else:
             ach = tv["bytes"] / tv["ms"] / 1e6
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['source']} copy"}
+                        "frac": ach / peaks["hbm"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                        "peak_source": f"{peaks['source']} copy"}
     whole_net = {
         "tflops": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 * world / world,
         "frac_of_tensor_peak": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 / peaks["tf_sust"],

@@ -6,7 +6,7 @@ Public surface (BASELINE.json north_star):
 Everything computes in hand-written sm_100a CUDA kernels behind the C ABI in
 include/golfer_b200.h; there is no CPU fallback.
 """
-from . import config, params  # noqa: F401
+from . import config, params, shard  # noqa: F401
 from .config import V0, V0_STRESS, GolfSegConfig  # noqa: F401
 from .host import (  # noqa: F401
     GolferError,
