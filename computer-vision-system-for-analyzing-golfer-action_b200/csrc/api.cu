@@ -378,13 +378,21 @@ int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8
     const size_t out_per = (size_t)T * c.num_classes;
     // Clips are independent: split the batch in chunks; H2D of chunk i+1 (copy stream)
     // overlaps the kernels of chunk i (compute stream); D2H follows each chunk.
-    // four chunks measured best at B = 256 (33.0 k clips/s vs 30.8 k with two); GOLFER_HOST_CHUNKS overrides
+    // Chunk schedule: a small first chunk gets the kernels started early, the rest follows in equal parts
+    // (GOLFER_HOST_CHUNKS = number of chunks, GOLFER_HOST_FIRST = clips in the first chunk).
     static const int env_chunks = getenv("GOLFER_HOST_CHUNKS") ? atoi(getenv("GOLFER_HOST_CHUNKS")) : 0;
-    const int nchunks = env_chunks > 0 ? (env_chunks < B ? env_chunks : B) : (B >= 8 ? 4 : 1);
-    const int per = (B + nchunks - 1) / nchunks;
+    static const int env_first = getenv("GOLFER_HOST_FIRST") ? atoi(getenv("GOLFER_HOST_FIRST")) : 0;
+    // measured at B = 256 (e2e clips/s): 1 chunk 42.8 k, 2 equal 42.1 k, 2 with a quarter first 43.2 k,
+    // 3 chunks 35-41 k, 4 equal 37.4 k: the persistent kernels lose efficiency on small batches faster than
+    // the 15.7 MB input copy (~0.35 ms) is worth hiding
+    const int nchunks = env_chunks > 0 ? (env_chunks < B ? env_chunks : B) : (B >= 16 ? 2 : 1);
+    int first = env_first > 0 && env_first < B && nchunks > 1 ? env_first
+                                                               : (env_chunks > 0 ? (B + nchunks - 1) / nchunks : (B >= 16 ? B / 4 : B));
+    const int rest = nchunks > 1 ? (B - first + nchunks - 2) / (nchunks - 1) : B;
     cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
     GS_CUDA(cudaEventRecord(ctx->ev_start, sc));
-    for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+    for (int k = 0, b0 = 0; b0 < B; ++k) {
+        const int per = k == 0 ? first : rest;
         const int nb = (B - b0) < per ? (B - b0) : per;
         const int e = k & 1;
         GS_CUDA(cudaMemcpyAsync(ctx->d_skel + b0 * in_per, skel_host + b0 * in_per, nb * in_per * 4,
@@ -401,6 +409,7 @@ int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8
         if (labels_host)
             GS_CUDA(cudaMemcpyAsync(labels_host + (size_t)b0 * T, ctx->d_labels + (size_t)b0 * T, (size_t)nb * T,
                                     cudaMemcpyDeviceToHost, sc));
+        b0 += nb;
     }
     GS_CUDA(cudaEventRecord(ctx->ev_stop, sc));
     ctx->ev_valid = true;

@@ -18,11 +18,15 @@
 // TMEM map (512 columns): accumulator(s) from column 0 (two of them when 2C <= 256),
 // [256,320) D1, [320,512) Abig_0..2.
 //
-// Warp roles (512 threads, persistent, 1 CTA/SM):
+// Warp roles (896 threads, persistent, 1 CTA/SM):
 //   w0 input-box TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
-//   w4-7   convert warps : build Abig (once), D1 -> bf16 XA chunks
-//   w8-11  gate warps    : multiply each landed box by gT*gV in place, TMA-store it as Xg
-//   w12-15 epilogue warps: acc -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store of Y
+//   w4-11  convert warps : build Abig (once, w4-7), D1 -> bf16 XA chunks; warps w and w+4 share TMEM
+//                          lanes and take 32 of D1's 64 columns each
+//   w12-19 gate warps    : multiply each landed box by gT*gV in place, TMA-store it as Xg
+//   w20-27 epilogue warps: acc -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store of Y, 32 columns
+//                          of each 64-column box per warp
+// Measured before the split (4 warps per role, 64 columns per thread): convert 800-1100 cycles per
+// chunk against 896 of tensor work at C=256, gate 3000 cycles per box, epilogue 1700 per box.
 // The input tile moves through a RING of 64-channel boxes (X box + its gT / gV slices, all three
 // brought by TMA); a box is released after its three MMA1s (chunk order: box-major, partition
 // minor), so the next tile's boxes load and get gated while this tile is still in the MMAs.
@@ -34,7 +38,8 @@ namespace gcn {
 
 using namespace tc;
 
-constexpr int kThreadsGcn = 512;
+constexpr int kThreadsGcn = 896;
+constexpr int kRoleThreads = 256;   // convert / gate / epilogue: 8 warps each
 constexpr int kFramesPerTile = 7;
 constexpr int kRowsPerTile = kFramesPerTile * 17;   // 119
 constexpr int kColD1 = 256;
@@ -116,7 +121,7 @@ __host__ __device__ inline Smem smem_layout(int C, int xslots, int wstages, int 
     s.xa_off = s.w_off + s.w_stage_bytes * wstages;
     s.epi_off = s.xa_off + 2u * 16384u;
     s.bar_off = s.epi_off + (uint32_t)eslots * 16384u;
-    s.total = s.bar_off + 512 + 1024;
+    s.total = s.bar_off + 512 + 1024 /*bias[C <= 256]*/ + 1024;
     return s;
 }
 
@@ -173,12 +178,12 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mbar_init(&w_empty[s], 1);
         }
         mbar_init(d1_full, 1);
-        mbar_init(d1_empty, 128);
+        mbar_init(d1_empty, kRoleThreads);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&xa_full[s], 128);
+            mbar_init(&xa_full[s], kRoleThreads);
             mbar_init(&xa_empty[s], 1);
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], kRoleThreads);
         }
         fence_barrier_init();
     }
@@ -188,6 +193,8 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    float *sbias = reinterpret_cast<float *>(smem + lay.bar_off + 512);
+    for (int k = threadIdx.x; k < C; k += kThreadsGcn) sbias[k] = prm.bias[k];
     // ---- one-time: block-diagonal adjacency Abig_p = I_7 (x) A_p into tensor memory --------
     if (warp >= 4 && warp < 8) {
         const int r = (warp - 4) * 32 + lane;          // output row (w of frame f)
@@ -321,21 +328,20 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             __syncwarp();
             ++acc_cnt;
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== convert warps: D1 (fp32, TMEM) -> bf16 XA chunk in swizzled smem =====
-        const int ew = warp - 4;
+    } else if (warp >= 4 && warp < 12) {
+        // ===== convert warps: D1 (fp32, TMEM) -> bf16 XA chunk in swizzled smem; 32 columns per warp =====
+        const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
         const int r = ew * 32 + lane;
         const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
         uint32_t d1_cnt = 0, xa_cnt = 0;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
             for (int q = 0; q < nq; ++q) {
-                uint32_t v[64];
+                uint32_t v[32];
                 mbar_wait(d1_full, d1_cnt & 1);
                 if (threadIdx.x == 128) GCN_TRACE(2, tcount, q);
                 tc_fence_after();
-                tmem_ld32(tmem_base + lane_base + kColD1, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld32(tmem_base + lane_base + kColD1 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld32(tmem_base + lane_base + kColD1 + (uint32_t)(half * 32), v);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(d1_empty);              // D1 may be overwritten by the next MMA1
@@ -345,12 +351,13 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 if (threadIdx.x == 128) GCN_TRACE(2, tcount, 16 + q);
                 unsigned char *box = smem + lay.xa_off + slot * 16384u;
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int cc = half * 4 + c4;
                     uint4 pk;
-                    pk.x = pack_bf16(__uint_as_float(v[cc * 8 + 0]), __uint_as_float(v[cc * 8 + 1]));
-                    pk.y = pack_bf16(__uint_as_float(v[cc * 8 + 2]), __uint_as_float(v[cc * 8 + 3]));
-                    pk.z = pack_bf16(__uint_as_float(v[cc * 8 + 4]), __uint_as_float(v[cc * 8 + 5]));
-                    pk.w = pack_bf16(__uint_as_float(v[cc * 8 + 6]), __uint_as_float(v[cc * 8 + 7]));
+                    pk.x = pack_bf16(__uint_as_float(v[c4 * 8 + 0]), __uint_as_float(v[c4 * 8 + 1]));
+                    pk.y = pack_bf16(__uint_as_float(v[c4 * 8 + 2]), __uint_as_float(v[c4 * 8 + 3]));
+                    pk.z = pack_bf16(__uint_as_float(v[c4 * 8 + 4]), __uint_as_float(v[c4 * 8 + 5]));
+                    pk.w = pack_bf16(__uint_as_float(v[c4 * 8 + 6]), __uint_as_float(v[c4 * 8 + 7]));
                     *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
                     if (prm.dbg_xa)
                         *reinterpret_cast<uint4 *>(prm.dbg_xa + ((size_t)tile * 128 + r) * (size_t)(3 * Cin) +
@@ -362,9 +369,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 ++xa_cnt;
             }
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 12 && warp < 20) {
         // ===== gate warps: Xg = X * gT * gV in place (gates read from the slot), TMA-store Xg =====
-        const int gt_id = threadIdx.x - 256;          // 0..127
+        const int gt_id = threadIdx.x - 384;          // 0..255
         const bool leader = (gt_id == 0);
         int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
@@ -379,7 +386,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][64]
                     const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][64]
 #pragma unroll 2
-                    for (int idx = gt_id; idx < kTileM * 8; idx += 128) {
+                    for (int idx = gt_id; idx < kTileM * 8; idx += kRoleThreads) {
                         const int r = idx >> 3, cc = idx & 7;
                         if (row0 + r >= prm.rows_per_clip) continue;     // TMA zero-filled rows
                         const int f = r / 17, v = r - f * 17;
@@ -399,7 +406,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     }
                     fence_proxy_async_smem();
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (leader) {
                     mbar_arrive(&x_ready[slot]);
                     GCN_TRACE(3, tcount, 16 + cb);
@@ -421,11 +428,11 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             if (prev_slot >= 0) mbar_arrive(&x_empty[prev_slot]);
             tma_store_wait_all0();
         }
-    } else if (warp >= 12) {
-        // ===== epilogue warps: acc -> +bias, ReLU -> bf16 -> staging ring -> TMA store =====
-        const int ew = warp - 12;
+    } else if (warp >= 20) {
+        // ===== epilogue warps: acc -> +bias, ReLU -> bf16 -> staging ring -> TMA store; 32 columns per warp =====
+        const int ew = (warp - 20) & 3, half = (warp - 20) >> 2;
         const int r = ew * 32 + lane;
-        const bool leader = (threadIdx.x == 384);
+        const bool leader = (threadIdx.x == 640);
         const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
         uint32_t acc_cnt = 0, ecnt = 0;
         int tcount = 0;
@@ -437,10 +444,8 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             if (leader) GCN_TRACE(4, tcount, 0);
             tc_fence_after();
             for (int qb = 0; qb < C / 64; ++qb) {
-                uint32_t v[64];
-                const uint32_t ta = tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64);
-                tmem_ld32(ta, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld32(ta + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64 + half * 32), v);
                 tmem_ld_wait();
                 if (qb == C / 64 - 1) {
                     tc_fence_before();
@@ -452,23 +457,22 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 unsigned char *box = smem + lay.epi_off + es * 16384u;
+                const float *bq = sbias + qb * 64 + half * 32;
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        f[e] = fmaxf(__uint_as_float(v[cc * 8 + e]) + __ldg(prm.bias + qb * 64 + cc * 8 + e), 0.f);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bq + c4 * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bq + c4 * 8 + 4);
                     uint4 pk;
-                    pk.x = pack_bf16(f[0], f[1]);
-                    pk.y = pack_bf16(f[2], f[3]);
-                    pk.z = pack_bf16(f[4], f[5]);
-                    pk.w = pack_bf16(f[6], f[7]);
-                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+                    pk.x = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 1]) + b0.y, 0.f));
+                    pk.y = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 3]) + b0.w, 0.f));
+                    pk.z = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 5]) + b1.y, 0.f));
+                    pk.w = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 7]) + b1.w, 0.f));
+                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + (((half * 4 + c4) ^ (r & 7)) << 4)) = pk;
                 }
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (leader) {
                     tma_store_3d(&mapY, box, qb * 64, row0, b);
                     tma_store_commit();
@@ -498,10 +502,16 @@ struct LaunchGcn {
 // stream), then as many input boxes as remain (at least 3).
 inline bool plan_smem(Params &p) {
     p.nacc = (2 * p.C <= 256) ? 2 : 1;
+    static const int env_ws = getenv("GOLFER_GCN_WS") ? atoi(getenv("GOLFER_GCN_WS")) : 0;
+    static const int env_es = getenv("GOLFER_GCN_ES") ? atoi(getenv("GOLFER_GCN_ES")) : 0;
     const int es_c[2] = {2, 1};
     const int ws_c[3] = {4, 3, 2};
-    for (int ws : ws_c)
-        for (int es : es_c)
+    // two staging slots first (measured: the store of box n draining behind box n+1 is worth more than a
+    // deeper weight ring), then the deepest weight ring, then as many input boxes as remain
+    for (int es : es_c) {
+        if (env_es && es != env_es) continue;
+        for (int ws : ws_c) {
+            if (env_ws && ws != env_ws) continue;
             for (int xs = kMaxXSlots; xs >= 3; --xs) {
                 if (smem_layout(p.C, xs, ws, es).total <= 227u * 1024u) {
                     p.xslots = xs;
@@ -510,6 +520,8 @@ inline bool plan_smem(Params &p) {
                     return true;
                 }
             }
+        }
+    }
     return false;
 }
 

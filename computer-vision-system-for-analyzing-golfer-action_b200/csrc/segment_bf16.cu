@@ -286,6 +286,21 @@ int bf16_path_create(Ctx *ctx) {
     ctx->bf16 = bp;
     if (const char *e = getenv("GOLFER_GCN_UNFUSED")) bp->fused_gcn = !(e[0] == '1');
     if (const char *e = getenv("GOLFER_STJ_FFMA")) bp->stj_tc = !(e[0] == '1');
+    if (const char *e = getenv("GOLFER_DEBUG_XA")) bp->debug_xa = (e[0] == '1');
+    if (const char *e = getenv("GOLFER_TRACE_GCN")) {
+        if (e[0] == '1') {
+            const size_t n = (size_t)GS_MAX_BLOCKS * 5 * gcn::kTraceTiles * gcn::kTraceEv;
+            GS_CUDA(cudaMalloc((void **)&bp->trace, n * 8));
+            GS_CUDA(cudaMemset(bp->trace, 0, n * 8));
+        }
+    }
+    if (const char *e = getenv("GOLFER_TRACE_TC")) {
+        if (e[0] == '1') {
+            const size_t n = (size_t)GS_MAX_BLOCKS * 2 * 5 * tc::kTraceTiles * tc::kTraceEv;
+            GS_CUDA(cudaMalloc((void **)&bp->trace_tc, n * 8));
+            GS_CUDA(cudaMemset(bp->trace_tc, 0, n * 8));
+        }
+    }
     const size_t nb = ctx->blocks.size();
     bp->WgT.assign(nb, nullptr);
     bp->W1T.assign(nb, nullptr);
