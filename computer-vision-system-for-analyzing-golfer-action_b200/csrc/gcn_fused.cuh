@@ -18,13 +18,19 @@
 // TMEM map (512 columns): accumulator(s) from column 0 (two of them when 2C <= 256),
 // [256,320) D1, [320,512) Abig_0..2.
 //
-// Warp roles (896 threads, persistent, 1 CTA/SM):
+// Warp roles (1024 threads, persistent, 1 CTA/SM):
 //   w0 input-box TMA producer   w1 MMA issuer   w2 TMEM alloc   w3 weight-ring TMA producer
 //   w4-11  convert warps : build Abig (once, w4-7), D1 -> bf16 XA chunks; warps w and w+4 share TMEM
 //                          lanes and take 32 of D1's 64 columns each
-//   w12-19 gate warps    : multiply each landed box by gT*gV in place, TMA-store it as Xg
-//   w20-27 epilogue warps: acc -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store of Y, 32 columns
-//                          of each 64-column box per warp
+//   w12-15 gate warps    : multiply each landed box by gT*gV in place, TMA-store it as Xg
+// (role split measured: convert 8 / gate 4 / epilogue 16 = 1.94 ms per step over the 5 launches;
+//  8/8/8 = 1.98; 4/8/16 = 2.00)
+//   w16-31 epilogue warps: 16 columns of every 64-column box per warp.  A thread first DRAINS its share of
+//                          the whole accumulator into registers (+bias, ReLU, packed bf16: 8 registers per
+//                          box) and hands the accumulator back, then stages and TMA-stores box by box.  At
+//                          C = 256 there is room for ONE accumulator in tensor memory, so the drain time is
+//                          what the next tile's MMA2 waits for: ~400 cycles this way, ~6000 when each box was
+//                          staged before the next was read.
 // Measured before the split (4 warps per role, 64 columns per thread): convert 800-1100 cycles per
 // chunk against 896 of tensor work at C=256, gate 3000 cycles per box, epilogue 1700 per box.
 // The input tile moves through a RING of 64-channel boxes (X box + its gT / gV slices, all three
@@ -38,8 +44,10 @@ namespace gcn {
 
 using namespace tc;
 
-constexpr int kThreadsGcn = 896;
-constexpr int kRoleThreads = 256;   // convert / gate / epilogue: 8 warps each
+constexpr int kThreadsGcn = 1024;
+constexpr int kRoleThreads = 256;   // convert: 8 warps
+constexpr int kGateThreads = 128;   // gate: 4 warps
+constexpr int kEpiThreads = 512;    // epilogue: 16 warps
 constexpr int kFramesPerTile = 7;
 constexpr int kRowsPerTile = kFramesPerTile * 17;   // 119
 constexpr int kColD1 = 256;
@@ -93,6 +101,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 
 // MN-major (channels contiguous) SW128 operand: rows of the K dimension are 128 B apart, 8-row groups
 // 1024 B apart (SBO); LBO = distance between 64-element MN blocks (unused here: N = 64 = one block).
@@ -125,6 +142,14 @@ __host__ __device__ inline Smem smem_layout(int C, int xslots, int wstages, int 
     return s;
 }
 
+// packed fp32 multiply (sm_100 FMUL2): two IEEE-rounded products per instruction
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
@@ -183,7 +208,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mbar_init(&xa_full[s], kRoleThreads);
             mbar_init(&xa_empty[s], 1);
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kRoleThreads);
+            mbar_init(&acc_empty[s], kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -369,9 +394,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 ++xa_cnt;
             }
         }
-    } else if (warp >= 12 && warp < 20) {
+    } else if (warp >= 12 && warp < 16) {
         // ===== gate warps: Xg = X * gT * gV in place (gates read from the slot), TMA-store Xg =====
-        const int gt_id = threadIdx.x - 384;          // 0..255
+        const int gt_id = threadIdx.x - 384;          // 0..127
         const bool leader = (gt_id == 0);
         int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
@@ -385,8 +410,8 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 if (prm.gT) {
                     const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][64]
                     const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][64]
-#pragma unroll 2
-                    for (int idx = gt_id; idx < kTileM * 8; idx += kRoleThreads) {
+#pragma unroll 4
+                    for (int idx = gt_id; idx < kTileM * 8; idx += kGateThreads) {
                         const int r = idx >> 3, cc = idx & 7;
                         if (row0 + r >= prm.rows_per_clip) continue;     // TMA zero-filled rows
                         const int f = r / 17, v = r - f * 17;
@@ -395,18 +420,21 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         const float4 t0 = sgt[f * 16 + cc * 2], t1 = sgt[f * 16 + cc * 2 + 1];
                         const float4 v0 = sgv[v * 16 + cc * 2], v1 = sgv[v * 16 + cc * 2 + 1];
                         const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
-                        const float2 a = __bfloat1622float2(xp[0]), c2 = __bfloat1622float2(xp[1]);
-                        const float2 d = __bfloat1622float2(xp[2]), e = __bfloat1622float2(xp[3]);
+                        // (x * gT) * gV, same rounding order as the scalar form, two products per FMUL2
+                        const float2 a = fmul2(fmul2(__bfloat1622float2(xp[0]), make_float2(t0.x, t0.y)), make_float2(v0.x, v0.y));
+                        const float2 c2 = fmul2(fmul2(__bfloat1622float2(xp[1]), make_float2(t0.z, t0.w)), make_float2(v0.z, v0.w));
+                        const float2 d = fmul2(fmul2(__bfloat1622float2(xp[2]), make_float2(t1.x, t1.y)), make_float2(v1.x, v1.y));
+                        const float2 e = fmul2(fmul2(__bfloat1622float2(xp[3]), make_float2(t1.z, t1.w)), make_float2(v1.z, v1.w));
                         uint4 o;
-                        o.x = pack_bf16(a.x * t0.x * v0.x, a.y * t0.y * v0.y);
-                        o.y = pack_bf16(c2.x * t0.z * v0.z, c2.y * t0.w * v0.w);
-                        o.z = pack_bf16(d.x * t1.x * v1.x, d.y * t1.y * v1.y);
-                        o.w = pack_bf16(e.x * t1.z * v1.z, e.y * t1.w * v1.w);
+                        o.x = pack_bf16(a.x, a.y);
+                        o.y = pack_bf16(c2.x, c2.y);
+                        o.z = pack_bf16(d.x, d.y);
+                        o.w = pack_bf16(e.x, e.y);
                         *sp = o;
                     }
                     fence_proxy_async_smem();
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (leader) {
                     mbar_arrive(&x_ready[slot]);
                     GCN_TRACE(3, tcount, 16 + cb);
@@ -428,11 +456,11 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             if (prev_slot >= 0) mbar_arrive(&x_empty[prev_slot]);
             tma_store_wait_all0();
         }
-    } else if (warp >= 20) {
-        // ===== epilogue warps: acc -> +bias, ReLU -> bf16 -> staging ring -> TMA store; 32 columns per warp =====
-        const int ew = (warp - 20) & 3, half = (warp - 20) >> 2;
+    } else if (warp >= 16) {
+        // ===== epilogue warps: drain the accumulator to packed registers, release it, then stage + store =====
+        const int ew = (warp - 16) & 3, cq = (warp - 16) >> 2;      // TMEM lane quarter, 16-column quarter of a box
         const int r = ew * 32 + lane;
-        const bool leader = (threadIdx.x == 640);
+        const bool leader = (threadIdx.x == 512);
         const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
         uint32_t acc_cnt = 0, ecnt = 0;
         int tcount = 0;
@@ -443,41 +471,50 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mbar_wait(&acc_full[as], aph);
             if (leader) GCN_TRACE(4, tcount, 0);
             tc_fence_after();
-            for (int qb = 0; qb < C / 64; ++qb) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64 + half * 32), v);
-                tmem_ld_wait();
-                if (qb == C / 64 - 1) {
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[as]);     // accumulator fully read
-                }
-                const uint32_t es = ecnt % (uint32_t)ES;
-                // staging slot reuse: the store issued ES boxes ago must have finished reading it
-                if (leader && ecnt >= (uint32_t)ES) {
-                    if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                unsigned char *box = smem + lay.epi_off + es * 16384u;
-                const float *bq = sbias + qb * 64 + half * 32;
+            uint32_t pk[4][8];                       // up to 4 boxes (C <= 256) x 16 bf16
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 b0 = *reinterpret_cast<const float4 *>(bq + c4 * 8);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(bq + c4 * 8 + 4);
-                    uint4 pk;
-                    pk.x = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 1]) + b0.y, 0.f));
-                    pk.y = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 3]) + b0.w, 0.f));
-                    pk.z = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 5]) + b1.y, 0.f));
-                    pk.w = pack_bf16(fmaxf(__uint_as_float(v[c4 * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[c4 * 8 + 7]) + b1.w, 0.f));
-                    *reinterpret_cast<uint4 *>(box + (size_t)r * 128 + (((half * 4 + c4) ^ (r & 7)) << 4)) = pk;
+            for (int qb = 0; qb < 4; ++qb) {
+                if (qb < C / 64) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64 + cq * 16), v);
+                    tmem_ld_wait();
+                    const float *bq = sbias + qb * 64 + cq * 16;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bq + e * 4);
+                        pk[qb][2 * e] = pack_bf16(fmaxf(__uint_as_float(v[4 * e + 0]) + bb.x, 0.f),
+                                                  fmaxf(__uint_as_float(v[4 * e + 1]) + bb.y, 0.f));
+                        pk[qb][2 * e + 1] = pack_bf16(fmaxf(__uint_as_float(v[4 * e + 2]) + bb.z, 0.f),
+                                                      fmaxf(__uint_as_float(v[4 * e + 3]) + bb.w, 0.f));
+                    }
                 }
-                fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (leader) {
-                    tma_store_3d(&mapY, box, qb * 64, row0, b);
-                    tma_store_commit();
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);             // accumulator fully read: the next tile's MMA2 may start
+            if (leader) GCN_TRACE(4, tcount, 2);
+#pragma unroll
+            for (int qb = 0; qb < 4; ++qb) {
+                if (qb < C / 64) {
+                    const uint32_t es = ecnt % (uint32_t)ES;
+                    // staging slot reuse: the store issued ES boxes ago must have finished reading it
+                    if (leader && ecnt >= (uint32_t)ES) {
+                        if (ES == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    unsigned char *rowp = smem + lay.epi_off + es * 16384u + (size_t)r * 128;
+                    *reinterpret_cast<uint4 *>(rowp + (((cq * 2) ^ (r & 7)) << 4)) =
+                        make_uint4(pk[qb][0], pk[qb][1], pk[qb][2], pk[qb][3]);
+                    *reinterpret_cast<uint4 *>(rowp + (((cq * 2 + 1) ^ (r & 7)) << 4)) =
+                        make_uint4(pk[qb][4], pk[qb][5], pk[qb][6], pk[qb][7]);
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (leader) {
+                        tma_store_3d(&mapY, smem + lay.epi_off + es * 16384u, qb * 64, row0, b);
+                        tma_store_commit();
+                    }
+                    ++ecnt;
                 }
-                ++ecnt;
             }
             if (leader) GCN_TRACE(4, tcount, 1);
             ++acc_cnt;
