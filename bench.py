@@ -45,6 +45,11 @@ def parse_args():
                     choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--pairs", type=int, default=PAIRS)
+    ap.add_argument("--workload", default="segment", choices=["segment", "stress", "pipeline"],
+                    help="segment = BASELINE configs[1] (default, the contract line); stress = configs[4] "
+                         "(T=1800, 8 branches, 64 clips over the GPUs); pipeline = configs[3] (segment + align over "
+                         "--clips clips sharded over the GPUs, gathers inside)")
+    ap.add_argument("--clips", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-align", action="store_true")
     return ap.parse_args()
@@ -203,6 +208,60 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ pipeline ----
+def run_pipeline(args, golfer_b200, dist, dev, world, rank, local):
+    """BASELINE configs[3]: segment + align over `--clips` synthetic clips sharded over the GPUs (contiguous
+    shards, 256-clip batches), pairs = (clip 2i, clip 2i+1) cut to 300 frames, u8 labels and padded paths
+    gathered with NCCL after every batch.  One JSON line: whole-job clips/s and pairs/s."""
+    from golfer_b200.shard import shard_range
+    cfg = golfer_b200.V0
+    lo, hi = shard_range(args.clips, rank, world)
+    nb = BATCH
+    seg = golfer_b200.Segmenter(cfg, seed=1234, precision=args.precision, device=local, max_B=nb, max_T=T_FRAMES)
+    actx = golfer_b200.host.Context(local)
+    skel = synth_skel(nb, T_FRAMES, seed=rank).to(dev)          # one resident synthetic batch, reused
+    maxL = 2 * T_FRAMES - 1
+    glab = torch.empty((world * nb, T_FRAMES), dtype=torch.uint8, device=dev) if dist is not None else None
+    gpath = torch.empty((world * (nb // 2), maxL, 2), dtype=torch.int32, device=dev) if dist is not None else None
+
+    def batch_step():
+        logits, labels = seg.segment(skel, return_labels=True)
+        xy = skel[..., :2].contiguous()
+        cost, path, plen = golfer_b200.host.align_batch(xy[0::2], xy[1::2], ctx=actx)
+        if dist is not None:
+            dist.all_gather_into_tensor(glab, labels)
+            dist.all_gather_into_tensor(gpath, path)
+        return logits
+
+    for _ in range(max(args.warmup, 1)):
+        batch_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    nbatches = (hi - lo + nb - 1) // nb
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nbatches):
+        batch_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pipeline clips/sec (segment + align, T=300)", "value": args.clips / (ms * 1e-3), "unit": "clips/s",
+            "pairs_per_s": (args.clips // 2) / (ms * 1e-3), "n_gpus": world, "steps": nbatches, "warmup": max(args.warmup, 1),
+            "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: {args.clips} clips sharded over {world} GPU(s), 256-clip batches, "
+                                   "segment -> labels, align(clip 2i, clip 2i+1), NCCL all-gather of u8 labels and paths per batch"}}),
+            flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ GPU arm -----
 def main():
     args = parse_args()
@@ -222,6 +281,15 @@ def main():
     peaks = load_peaks()
     cfg = golfer_b200.V0
     B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    if args.workload == "pipeline":
+        return run_pipeline(args, golfer_b200, dist, dev, world, rank, local)
+    global T_FRAMES
+    if args.workload == "stress":       # BASELINE configs[4]: 1800-frame clips, 8 temporal branches, batch 64 over the GPUs
+        cfg = golfer_b200.V0_STRESS
+        T_FRAMES = 1800
+        B = max(64 // world, 1) if args.batch == BATCH else args.batch
+        args.no_align = True
+        args.no_cpu_baseline = True
 
     def barrier():
         torch.cuda.synchronize()
@@ -396,7 +464,8 @@ def main():
             "ms_per_step": seg_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"segmentation net fwd (GolfSegConfig {cfg.version} {cfg.config_hash()}), "
-                                   f"{B} clips/GPU x {T_FRAMES} frames x 17 joints x 3 ch (BASELINE configs[1])",
+                                   f"{B} clips/GPU x {T_FRAMES} frames x 17 joints x 3 ch "
+                                   f"(BASELINE configs[{4 if args.workload == 'stress' else 1}])",
                        "global_batch": world * B, "frames": T_FRAMES, "parallelism": f"dp{world}",
                        "l2_policy": "per-step working set (activations, several hundred MB) exceeds the 126 MB L2",
                        "collective": "all_gather(logits) inside each step" if world > 1 else "none"},

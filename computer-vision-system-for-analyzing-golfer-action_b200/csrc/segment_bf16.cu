@@ -21,11 +21,11 @@
 namespace gs {
 
 struct BlockMaps {
-    CUtensorMap xa_in, y_out, y_in, h_out, h_in, xg_in, u_out[2];
+    CUtensorMap xa_in, y_out, y_in;
     CUtensorMap h_out_jm;                                        // 1x1 GEMM store into joint-major H [B,V,T,C]
     tw::Maps tw;                                                 // sliding-window temporal conv
     CUtensorMap f_x_load, f_xg_store, f_y_store, f_gt, f_gv;    // fused GCN kernel (7-frame tiles)
-    CUtensorMap wg, w1, w2, wr;
+    CUtensorMap wg, w1;
 };
 
 struct Bf16Path {
@@ -173,10 +173,7 @@ int build_maps(Ctx *ctx, int T) {
         const int C = b.c, cin = b.cin, cr = b.cr;
         if ((rc = tc::make_act_map(&m.y_out, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
         if ((rc = tc::make_act_map(&m.y_in, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
-        if ((rc = tc::make_act_map(&m.h_out, ctx->bufH, C, rows, batch, 64, tc::kTileM))) return rc;
-        if ((rc = tc::make_act_map(&m.h_in, ctx->bufH, C, rows, batch, cr, tc::kTileM))) return rc;
-        for (int k = 0; k < 2; ++k)
-            if ((rc = tc::make_act_map(&m.u_out[k], ctx->bufU[k], C, rows, batch, 64, tc::kTileM))) return rc;
+        const int crm = cr < 16 ? 16 : cr;      // MMA width of a branch tap (tconv_window.cuh)
         {   // temporal conv: joint-major H, window loads, (C,V,T,B) views of the [B,T,V,C] tensors
             int dmax = 1;
             for (int r = 0; r < R; ++r) dmax = dmax > ctx->cfg.dilations[r] ? dmax : ctx->cfg.dilations[r];
@@ -188,7 +185,7 @@ int build_maps(Ctx *ctx, int T) {
             if ((rc = tw::make_btvc_joint_map(&m.tw.res, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, tw::kFramesTile)))
                 return rc;
             m.tw.xg = m.tw.res;
-            if ((rc = tc::make_weight_map(&m.tw.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
+            if ((rc = tc::make_weight_map(&m.tw.w2, bp->W2p[i], crm, R * 3 * crm, crm, crm))) return rc;
             m.tw.wr = m.tw.w2;
             if (proj) {
                 if ((rc = tw::make_btvc_joint_map(&m.tw.xg, ctx->bufX, cin, T, batch, 64, tw::kFramesTile))) return rc;
@@ -196,7 +193,6 @@ int build_maps(Ctx *ctx, int T) {
             }
         }
         if ((rc = tc::make_weight_map(&m.w1, bp->W1T[i], C, C, 64, C))) return rc;
-        if ((rc = tc::make_weight_map(&m.w2, bp->W2p[i], cr, R * 3 * cr, cr, cr))) return rc;
         if (i > 0) {
             if ((rc = tc::make_act_map(&m.xa_in, ctx->bufXA, 3 * cin, rows, batch, 64, tc::kTileM))) return rc;
             if ((rc = tc::make_weight_map(&m.wg, bp->WgT[i], 3 * cin, C, 64, C))) return rc;
@@ -205,10 +201,6 @@ int build_maps(Ctx *ctx, int T) {
             if ((rc = tc::make_act_map(&m.f_y_store, ctx->bufY, C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
             if ((rc = tc::make_f32_map(&m.f_gt, ctx->gT, cin, (long long)batch * T, 64, 8))) return rc;
             if ((rc = tc::make_f32_map(&m.f_gv, ctx->gV, cin, (long long)batch * V17, 64, V17))) return rc;
-            if (b.has_res) {
-                if ((rc = tc::make_act_map(&m.xg_in, ctx->bufX, cin, rows, batch, cr, tc::kTileM))) return rc;
-                if ((rc = tc::make_weight_map(&m.wr, bp->WrT[i], cin, C, cr, C))) return rc;
-            }
         }
     }
     bp->maps_T = T;
@@ -266,15 +258,11 @@ int bf16_path_create(Ctx *ctx) {
     }
     for (size_t i = 0; i < ctx->blocks.size(); ++i) {
         const BlockParams &b = ctx->blocks[i];
-        const bool ok = (b.c % 64 == 0) && b.c <= 256 && (b.cr == 16 || b.cr == 32 || b.cr == 64) &&
-                        (i == 0 || (b.cin % 64 == 0 && b.cin % b.cr == 0));
+        const bool ok = (b.c % 64 == 0) && b.c <= 256 && (b.cr == 8 || b.cr == 16 || b.cr == 32 || b.cr == 64) &&
+                        (i == 0 || b.cin % 64 == 0);
         if (!ok) {
-            set_error("bf16 tensor-core path needs widths in {64,128,256} and C/R in {16,32,64} "
+            set_error("bf16 tensor-core path needs widths in {64,128,256} and C/R in {8,16,32,64} "
                       "(block %zu: cin=%d c=%d c/R=%d); use precision fp32 for this config", i, b.cin, b.c, b.cr);
-            return GS_ERR_UNSUPPORTED;
-        }
-        if ((b.has_res ? b.cin / b.cr : 0) + 3 * R > tc::kMaxChunks) {
-            set_error("chunk program too long for block %zu", i);
             return GS_ERR_UNSUPPORTED;
         }
     }
@@ -329,14 +317,18 @@ int bf16_path_create(Ctx *ctx) {
                 for (int n = 0; n < C; ++n) h[(size_t)n * C + k] = __float2bfloat16_rn(W[(size_t)k * C + n]);
             if ((rc = upload_bf16(ctx, h, &bp->W1T[i]))) return rc;
         }
-        {   // W2p [(r*3+j)*cr + co][ci]
+        {   // W2p [(r*3+j)*crm + co'][ci'], crm = max(cr, 16): an 8-channel branch sits in its diagonal 8x8
+            // block of a zeroed 16x16 box (the other branch of the pair owns the other diagonal block)
             const float *W = host(b.W2);
-            h.assign((size_t)R * 3 * cr * cr, __nv_bfloat16());
-            for (int rj = 0; rj < R * 3; ++rj)
+            const int crm = cr < 16 ? 16 : cr;
+            h.assign((size_t)R * 3 * crm * crm, __float2bfloat16_rn(0.f));
+            for (int rj = 0; rj < R * 3; ++rj) {
+                const int off = ((rj / 3) * cr) % crm;
                 for (int ci = 0; ci < cr; ++ci)
                     for (int co = 0; co < cr; ++co)
-                        h[((size_t)rj * cr + co) * cr + ci] =
+                        h[((size_t)rj * crm + off + co) * crm + off + ci] =
                             __float2bfloat16_rn(W[((size_t)rj * cr + ci) * cr + co]);
+            }
             if ((rc = upload_bf16(ctx, h, &bp->W2p[i]))) return rc;
         }
         std::vector<float> bias(host(b.b2), host(b.b2) + C);

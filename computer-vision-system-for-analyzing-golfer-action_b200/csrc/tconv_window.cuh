@@ -78,8 +78,11 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-// CR = channels per branch (16 / 32 / 64): compile-time so the tap loop of the MMA issuer is straight-line
-// code (12 tcgen05.mma per step with loop-invariant operand offsets).
+// CR = channels per branch (8 / 16 / 32 / 64): compile-time so the tap loop of the MMA issuer is straight-line
+// code (12 tcgen05.mma per step with loop-invariant operand offsets; 24 for CR = 8).  A bf16 MMA needs
+// K = 16 and N % 16 == 0, so 8-channel branches (the R = 8 stress config at C = 64) run as 16-wide MMAs over
+// the pair of branches that shares a 16-channel slice: the host packs each branch's 8x8 tap into its
+// diagonal block of a zeroed 16x16 box, and the two branches accumulate into the same 16 columns.
 template <int CR>
 __global__ void __launch_bounds__(kTwThreads, 1)
 tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Params prm) {
@@ -102,6 +105,7 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
     const int ctas_per_box = gridDim.x / prm.nboxes;
     const int T = prm.T;
     constexpr int cr = CR, NBR = 64 / CR;
+    constexpr int CRM = CR < 16 ? 16 : CR;          // MMA width (K and N) per branch tap
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.h_win);
@@ -145,8 +149,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
             mbar_expect_tx(wres, prm.w_bytes + prm.wr_bytes);
             for (int rl = 0; rl < NBR; ++rl)
                 for (int j = 0; j < 3; ++j)
-                    tma_load_2d(smem + prm.w_off + (size_t)(rl * 3 + j) * (cr * cr * 2), &maps.w2, wres, 0,
-                                ((q * NBR + rl) * 3 + j) * cr);
+                    tma_load_2d(smem + prm.w_off + (size_t)(rl * 3 + j) * (CRM * CRM * 2), &maps.w2, wres, 0,
+                                ((q * NBR + rl) * 3 + j) * CRM);
             for (int kx = 0; kx < (prm.proj ? prm.nkx : 0); ++kx)
                 tma_load_2d(smem + prm.wr_off + (size_t)kx * 8192, &maps.wr, wres, kx * 64, q * 64);
         }
@@ -179,24 +183,25 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
         int stage = 0;
         uint32_t phase = 0;
         uint32_t ng[2] = {0, 0};                 // steps issued per group
-        constexpr uint32_t wrow_bytes = (uint32_t)CR * 2;
-        constexpr int ksteps = CR / 16;
-        const uint32_t idesc_tap = make_idesc_bf16((uint32_t)cr);
+        constexpr uint32_t wrow_bytes = (uint32_t)CRM * 2;
+        constexpr int ksteps = CRM / 16;
+        const uint32_t idesc_tap = make_idesc_bf16((uint32_t)CRM);
         const uint32_t idesc_proj = make_idesc_bf16(64u);
         // Everything that does not depend on the stage is computed ONCE: per (branch, tap) the byte offset of
         // the A start row inside the window and the weight descriptor; per step an MMA costs one 64-bit add.
         // (Descriptors rebuilt next to every tcgen05.mma cost ~200 cycles each through the uniform datapath.)
-        uint32_t aoff[12], dcol[12];
-        uint64_t dbv[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int rl = i / 3, j = i % 3;
-            const int d = rl < NBR ? prm.dil[q * NBR + rl] : 0;
-            aoff[i] = ((uint32_t)(prm.dmax + (j - 1) * d) * 128u + (uint32_t)(rl * cr * 2)) >> 4;
-            dcol[i] = (uint32_t)(rl * cr);
-            dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w_off + (size_t)i * (cr * cr * 2)), wrow_bytes);
-        }
         constexpr int ntap = 3 * NBR;
+        uint32_t aoff[ntap], dcol[ntap];
+        uint64_t dbv[ntap];
+#pragma unroll
+        for (int i = 0; i < ntap; ++i) {
+            const int rl = i / 3, j = i % 3;
+            const int d = prm.dil[q * NBR + rl];
+            const int ch0 = (rl * CR / CRM) * CRM;      // first channel of the MMA slice this branch lives in
+            aoff[i] = ((uint32_t)(prm.dmax + (j - 1) * d) * 128u + (uint32_t)(ch0 * 2)) >> 4;
+            dcol[i] = (uint32_t)ch0;
+            dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w_off + (size_t)i * (CRM * CRM * 2)), wrow_bytes);
+        }
         mbar_wait(wres, 0);
         for (int i0 = first_item; i0 < prm.nq_items; i0 += item_stride) {
             for (int v = 0; v < 17; ++v) {
@@ -229,12 +234,13 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) {
-                        if (i < ntap) {
+                    for (int i = 0; i < ntap; ++i) {
+                        {
                             const uint64_t da = da0 + (uint64_t)aoff[i];
                             const uint64_t db = dbv[i];
                             const uint32_t tdr = td + dcol[i];
-                            const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0));
+                            // first tap of the first branch in a column slice overwrites, everything else accumulates
+                            const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0) | ((((i / 3) * CR) % CRM) != 0));
 #pragma unroll
                             for (int k = 0; k < ksteps; ++k) {
                                 const uint32_t acc_k = accum | (uint32_t)(k > 0);
@@ -489,7 +495,8 @@ inline bool plan(Params &p) {
     p.a_span = ((uint32_t)p.wrows * 128u + 1023u) & ~1023u;
     p.xg_off = p.a_span;
     p.stage_bytes = p.a_span + (p.proj ? (uint32_t)p.nkx * 16384u : 0u);
-    p.w_bytes = (uint32_t)(p.nbr * 3 * p.cr * p.cr * 2);
+    const int crm = p.cr < 16 ? 16 : p.cr;
+    p.w_bytes = (uint32_t)(p.nbr * 3 * crm * crm * 2);
     p.wr_bytes = p.proj ? (uint32_t)p.nkx * 8192u : 0u;
     const uint32_t wspan = ((p.w_bytes + 1023u) & ~1023u) + p.wr_bytes;
     // three staging slots per group give the residual box two steps of lookahead (its TMA latency is about
@@ -529,7 +536,9 @@ inline int launch(Ctx *ctx, int kid, LaunchTw &L, cudaStream_t st) {
     const int need = L.prm.nq_items * L.prm.nboxes;
     if (grid > need) grid = need;
     if (grid < 1) return GS_OK;
-    auto kern = L.prm.cr == 16 ? tconv_window_kernel<16> : (L.prm.cr == 32 ? tconv_window_kernel<32> : tconv_window_kernel<64>);
+    auto kern = L.prm.cr == 8 ? tconv_window_kernel<8>
+                              : (L.prm.cr == 16 ? tconv_window_kernel<16>
+                                                : (L.prm.cr == 32 ? tconv_window_kernel<32> : tconv_window_kernel<64>));
     GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.prm.total));
     {
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);

@@ -98,6 +98,23 @@ def test_fp32_odd_config_tiny_and_stress_branches():
         seg.ctx.close()
 
 
+@pytest.mark.parametrize("B,T", [(2, 45), (1, 300), (1, 1800)])
+def test_bf16_stress_config_eight_branches(B, T):
+    """BASELINE.json configs[4]: 8 temporal branches with dilations 1..8 (C/R = 8 at C = 64: 8-channel
+    branches run as paired 16-wide MMAs), up to 1800-frame clips (15 frame tiles, 17-frame halo)."""
+    cfg = golfer_b200.V0_STRESS
+    params = golfer_b200.params.make_params(cfg, 1234)
+    skel = osegnet.synth_skeletons(B, T, cfg, seed=T + B)
+    want = osegnet.segment_ref(cfg, params, skel)
+    seg = golfer_b200.Segmenter(cfg, params, precision="bf16", max_B=B, max_T=T)
+    logits, labels = seg.segment(torch.from_numpy(skel).cuda(), return_labels=True)
+    err = _rel(logits.cpu().numpy(), want)
+    print(f"stress bf16 B={B} T={T}: rel err {err:.3e}")
+    assert err < TOL["bf16"]
+    _label_check(want, labels.cpu().numpy(), TOL["bf16"])
+    seg.ctx.close()
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_host_entry_point_equals_device_entry_point(prec):
     cfg = golfer_b200.V0
