@@ -437,10 +437,9 @@ inline void pack_stj_fragments(const float *W, int K, int N, int nt, int npass, 
 
 // ---- head (README.md:17-18) -----------------------------------------------------------
 // logits[b,t,k] = sum_c (gT[b,t,c] * sum_v U[b,t,v,c]*gV[b,v,c] / V) * Wh[c,k] + bh[k]
-// One WARP per frame (8 warps, kHeadFrames frames of one clip per CTA); a lane owns 8-channel
-// vectors (16 B of bf16 per load).  gV[b] and the transposed head weights WhT [K][C] are staged
-// in shared memory once per CTA.  C % 8 == 0, K <= 32.
-constexpr int kHeadFrames = 16;
+// gV[b] and the transposed head weights WhT [K][C] are staged in shared memory once per CTA of
+// kHeadFrames frames of one clip.  C % 8 == 0, K <= 32.
+constexpr int kHeadFrames = 32;
 
 template <typename TU> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
@@ -463,6 +462,9 @@ template <> struct Vec8<float> {
     }
 };
 
+// A warp owns 4 frames: lane = (frame f = lane / 8, channel group g = lane % 8); a lane walks the 8-channel
+// vectors g, g+8, ... of its frame, folds them straight into K logit partials, and the partials are reduced
+// over the 8 lanes of the frame (3 shuffle steps for 4 frames at once).  kHeadFrames = 32 frames per CTA.
 template <typename TU, int V>
 __global__ void __launch_bounds__(256)
 head_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const float *__restrict__ gV, int T, int C,
@@ -477,56 +479,55 @@ head_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const float 
     for (int e = threadIdx.x * 4; e < K * C; e += blockDim.x * 4)
         *reinterpret_cast<float4 *>(swh + e) = __ldg(reinterpret_cast<const float4 *>(WhT + e));
     __syncthreads();
-    for (int t = blockIdx.x * kHeadFrames + warp; t < min(T, (int)(blockIdx.x + 1) * kHeadFrames); t += 8) {
-        const size_t bt = (size_t)b * T + t;
-        float best = 0.f, mine = 0.f;     // lane k keeps logit k
-        for (int cb = 0; cb < C; cb += 256) {      // warp-uniform trip count: lanes past C add zeros
-            const int c0 = cb + lane * 8;
-            const bool on = c0 < C;
-            float acc[8];
+    const int f = lane >> 3, g = lane & 7;
+    const int t = blockIdx.x * kHeadFrames + warp * 4 + f;
+    const bool tv = t < T;
+    const size_t bt = (size_t)b * T + (tv ? t : T - 1);
+    float part[32];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-            if (on) {
-                const TU *row = U + (bt * V) * C + c0;
+    for (int k = 0; k < 32; ++k) part[k] = 0.f;
+    for (int c0 = g * 8; c0 < C; c0 += 64) {
+        float acc[8];
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    float x[8];
-                    Vec8<TU>::load(row + (size_t)v * C, x);
-                    const float4 g0 = *reinterpret_cast<const float4 *>(sgv + v * C + c0);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(sgv + v * C + c0 + 4);
-                    acc[0] += x[0] * g0.x; acc[1] += x[1] * g0.y; acc[2] += x[2] * g0.z; acc[3] += x[3] * g0.w;
-                    acc[4] += x[4] * g1.x; acc[5] += x[5] * g1.y; acc[6] += x[6] * g1.z; acc[7] += x[7] * g1.w;
-                }
-                float gt[8];
-                Vec8<float>::load(gT + bt * C + c0, gt);
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const TU *row = U + (bt * V) * C + c0;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = acc[e] * gt[e] / (float)V;
+        for (int v = 0; v < V; ++v) {
+            float x[8];
+            Vec8<TU>::load(row + (size_t)v * C, x);
+            const float4 g0 = *reinterpret_cast<const float4 *>(sgv + v * C + c0);
+            const float4 g1 = *reinterpret_cast<const float4 *>(sgv + v * C + c0 + 4);
+            acc[0] += x[0] * g0.x; acc[1] += x[1] * g0.y; acc[2] += x[2] * g0.z; acc[3] += x[3] * g0.w;
+            acc[4] += x[4] * g1.x; acc[5] += x[5] * g1.y; acc[6] += x[6] * g1.z; acc[7] += x[7] * g1.w;
+        }
+        float gt[8];
+        Vec8<float>::load(gT + bt * C + c0, gt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = acc[e] * gt[e] * (1.0f / (float)V);
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (k < K) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(swh + k * C + c0);
+                const float4 w1 = *reinterpret_cast<const float4 *>(swh + k * C + c0 + 4);
+                part[k] += acc[0] * w0.x + acc[1] * w0.y + acc[2] * w0.z + acc[3] * w0.w + acc[4] * w1.x +
+                           acc[5] * w1.y + acc[6] * w1.z + acc[7] * w1.w;
             }
-            for (int k = 0; k < K; ++k) {
-                float x = 0.f;
-                if (on) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(swh + k * C + c0);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(swh + k * C + c0 + 4);
-                    x = acc[0] * w0.x + acc[1] * w0.y + acc[2] * w0.z + acc[3] * w0.w + acc[4] * w1.x +
-                        acc[5] * w1.y + acc[6] * w1.z + acc[7] * w1.w;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == k) mine += x;
-            }
-        }
-        if (lane < K) {
-            mine += bh[lane];
-            logits[bt * K + lane] = mine;
-        }
-        // first arg-max over K (ties -> lowest class index), all lanes take part in the shuffles
-        int arg = 0;
-        for (int k = 0; k < K; ++k) {
-            const float x = __shfl_sync(0xffffffffu, mine, k);
-            if (k == 0 || x > best) { best = x; arg = k; }
-        }
-        if (labels && lane == 0) labels[bt] = (uint8_t)arg;
     }
+    // reduce over the 8 channel-group lanes of each frame; lane g == 0 of a frame ends with the totals
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) {
+            float x = part[k];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            x += bh[k];
+            if (g == 0 && tv) logits[bt * K + k] = x;
+            if (k == 0 || x > best) { best = x; arg = k; }      // first arg-max: ties -> lowest class index
+        }
+    if (labels && g == 0 && tv) labels[bt] = (uint8_t)arg;
 }
 
 // out[b,t,v,c] = U * gT * gV  (fp32; debug / parity hook)
