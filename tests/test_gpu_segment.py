@@ -53,7 +53,7 @@ def test_golden_fixtures(golden_dir, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("B,T", [(1, 300), (3, 37), (2, 5), (5, 64)])
+@pytest.mark.parametrize("B,T", [(1, 300), (3, 37), (2, 5), (5, 64), (1, 1), (2, 129), (1, 257)])
 def test_matches_oracle(prec, B, T):
     cfg = golfer_b200.V0
     params = golfer_b200.params.make_params(cfg, 1234)
