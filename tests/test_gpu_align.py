@@ -53,6 +53,32 @@ def test_generic_kernel_path_large_and_odd_joint_count():
     _check_against(a, b, cost, path, plen, rc, rp, rl)
 
 
+def test_sqrt_range_edges_bitwise():
+    # The wavefront kernel takes square roots with a packed refinement that is exact only for
+    # 2^-101 <= x < inf and falls back per frame otherwise: exercise both sides of every edge.
+    rng = np.random.default_rng(11)
+    a, b = oalign.synth_swings(8, 60, 70, seed=21)
+    b[0, :, 3] = a[0, :60, 3].mean(0)                 # pair 0: ordinary
+    b[1, :60] = a[1]                                  # pair 1: coincident joints on the diagonal (x = 0)
+    a[2] *= np.float32(2.0 ** -52); b[2] *= np.float32(2.0 ** -52)     # x around 2^-104: below the range
+    a[3] *= np.float32(2.0 ** -50); b[3] *= np.float32(2.0 ** -50)     # x straddling 2^-101
+    a[4] *= np.float32(2.0 ** -70); b[4] *= np.float32(2.0 ** -70)     # squares underflow to denormals / 0
+    a[5] *= np.float32(2.0 ** 62); b[5] *= np.float32(2.0 ** 62)       # x near 2^126: still finite
+    a[6] *= np.float32(2.0 ** 64); b[6] *= np.float32(2.0 ** 64)       # some squares overflow to inf
+    a[7, rng.integers(0, 60, 5), rng.integers(0, 17, 5), 0] = 0.0      # exact zeros against non-zeros
+    b[7, 10, 4] = a[7, 10, 4]                                           # one coincident joint in one frame
+    with np.errstate(over="ignore", invalid="ignore", under="ignore"):
+        ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    assert np.array_equal(cost.cpu().numpy(), ref_cost, equal_nan=True)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+    cm = golfer_b200.host.pair_cost(_dev(a), _dev(b)).cpu().numpy()
+    with np.errstate(over="ignore", invalid="ignore", under="ignore"):
+        for n in range(8):
+            assert np.array_equal(cm[n], oalign.pair_cost(a[n], b[n]), equal_nan=True), n
+
+
 def test_self_alignment_zero_cost_diagonal():
     a, _ = oalign.synth_swings(2, 300, 300, seed=9)
     cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(a))
