@@ -14,7 +14,7 @@ const char *kernel_name(int id) {
     static const char *names[K_COUNT] = {
         "aggregate_fp32", "gemm_gcn_fp32", "gemm_tcn1x1_fp32", "gemm_res_fp32", "tconv_fp32", "stats", "se_gate",
         "stj_gate", "head", "features", "dtw_wavefront", "dtw_generic", "pair_cost", "compare",
-        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc"};
+        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc", "dtw_backtrack"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 

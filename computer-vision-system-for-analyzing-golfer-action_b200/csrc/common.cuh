@@ -56,7 +56,7 @@ struct Bf16Path;   // segment_bf16.cu
 enum KernelId {
     K_AGG = 0, K_GEMM_GCN, K_GEMM_TCN1, K_GEMM_RES, K_TCONV, K_STATS, K_SE, K_STJ, K_HEAD, K_FEAT,
     K_DTW, K_DTW_GENERIC, K_PAIRCOST, K_COMPARE,
-    K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC,
+    K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC, K_DTW_BACKTRACK,
     K_COUNT
 };
 const char *kernel_name(int id);
