@@ -346,8 +346,8 @@ int bf16_path_create(Ctx *ctx) {
             const float *srcs[3] = {host(b.jW), host(b.jWt), host(b.jWv)};
             for (int w = 0; w < 3; ++w) {
                 std::vector<float> packed;
-                if (w == 0) pack_stj_fragments(srcs[w], C, b.cj, Q, 1, packed);
-                else pack_stj_fragments(srcs[w], b.cj, C, Q == 1 ? 4 : 8, Q == 4 ? 2 : 1, packed);
+                if (w == 0) pack_stj_fragments(srcs[w], C, b.cj, Q == 1 ? 2 : 4, packed);
+                else pack_stj_fragments(srcs[w], b.cj, C, 4, packed);
                 for (float &x : packed) {      // round to nearest TF32 (10 explicit mantissa bits)
                     uint32_t u;
                     memcpy(&u, &x, 4);

@@ -273,12 +273,18 @@ stj_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const flo
 }
 
 // ---- ST-joint attention on warp-level tensor cores (bf16 path) ----------------------------------
-// Same math as stj_kernel with both small GEMMs as mma.sync m16n8k8 TF32 (fp32 accumulate): the FFMA
-// form is bound at ~70 us per C=256 launch by FMA issue alone.  One CTA = 64 positions of one clip;
-// 8 warps = 4 (16-row slabs) x 2 (column halves).  The three weight matrices are rounded to TF32 and
-// re-packed once at context creation, pooled / hidden activations are rounded when they are staged.
-// The fp32 parity path keeps stj_kernel (exact fp32).
+// Same math as stj_kernel with both small GEMMs as mma.sync m16n8k8 TF32 (fp32 accumulate).  The
+// launch is PERSISTENT: one CTA per SM keeps the first-layer matrix W and ONE second-layer matrix
+// (Wt for the frame CTAs, Wv for the joint CTAs) resident in shared memory in B-fragment order and
+// walks 64-position items, so the weights are read from L2 once per CTA instead of once per k-step
+// and warp (the per-item form was bound by those loads: 168 us per C=256 launch for 5 GFLOP and
+// 160 MB).  While an item is in the MMAs the next item's pooled rows are already in flight to
+// registers.  Items: frame item = 64 frames of one clip; joint item = the 17 joints of 3 clips.
+// 16 warps = 4 (16-row slabs) x 4 (column groups).  Weights are rounded to TF32 once at context
+// creation, activations when they are staged.  The fp32 parity path keeps stj_kernel (exact fp32).
 constexpr int kStjTcPos = 64;
+constexpr int kStjThreads = 512;
+constexpr int kStjClipsPerJointItem = 3;
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
@@ -292,147 +298,214 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// 1 / (1 + 2^(-x log2 e)) on the SFU approximations (rel. error ~1e-6, the bf16 path's bar is 1e-2)
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 
-// Q = cj / 16 with C = 64 * Q (ST-joint reduction 4).  Weights arrive re-packed in FRAGMENT ORDER
-// (host: pack_stj_fragments): for every k-step, column half and lane the B-fragment registers of all its
-// n-tiles are contiguous, so a warp fetches them with one or two 16-byte loads per lane (fully coalesced)
-// instead of 8-16 scalar loads of 32-byte segments.
+// Q = cj / 16 with C = 64 * Q (ST-joint reduction 4)
+template <int Q>
+struct StjCfg {
+    static constexpr int C = 64 * Q, CJ = 16 * Q;
+    static constexpr int WN1 = (CJ / 8 < 4) ? CJ / 8 : 4;   // column groups that work in the first GEMM
+    static constexpr int NT1 = CJ / 8 / WN1;                // n-tiles per warp, first GEMM
+    static constexpr int NT2 = 2 * Q;                       // n-tiles per warp, second GEMM (C/4 columns)
+    static constexpr int LDP = C + 4, LDA = CJ + 4;         // +4 floats: conflict-free A-fragment loads
+    static constexpr int NPF = kStjTcPos * C / 4 / kStjThreads;   // float4 per thread and item
+    static constexpr size_t smem_bytes =
+        ((size_t)2 * C * CJ + (size_t)kStjTcPos * (LDP + LDA) + CJ + 2 * C) * sizeof(float);
+};
+
 template <int V, int Q>
-__global__ void __launch_bounds__(256)
-stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const float *__restrict__ seS, int T,
-              int ntT, const float *__restrict__ P1, const float *__restrict__ bW, const float *__restrict__ P2t,
-              const float *__restrict__ bt, const float *__restrict__ P2v, const float *__restrict__ bv,
-              float *__restrict__ gT, float *__restrict__ gV) {
-    constexpr int C = 64 * Q, cj = 16 * Q;
-    constexpr int NT1 = Q;                       // n-tiles per warp, first GEMM (cj/2 columns)
-    constexpr int NT2 = Q == 1 ? 4 : 8;          // n-tiles per warp and pass, second GEMM
-    constexpr int NPASS = Q == 4 ? 2 : 1;        // passes of 64 columns over this warp's C/2 columns
-    constexpr int ldp = C + 4, lda = cj + 4;     // +4 floats: conflict-free A-fragment loads
+__global__ void __launch_bounds__(kStjThreads, 1)
+stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const float *__restrict__ seS, int B, int T,
+              int ntT, int ctasT, const float *__restrict__ P1, const float *__restrict__ bW,
+              const float *__restrict__ P2t, const float *__restrict__ bt, const float *__restrict__ P2v,
+              const float *__restrict__ bv, float *__restrict__ gT, float *__restrict__ gV) {
+    using Cf = StjCfg<Q>;
+    constexpr int C = Cf::C, cj = Cf::CJ, NT1 = Cf::NT1, NT2 = Cf::NT2, WN1 = Cf::WN1, ldp = Cf::LDP, lda = Cf::LDA;
+    constexpr int NPF = Cf::NPF, C4 = C / 4, KC = kStjClipsPerJointItem;
     extern __shared__ __align__(16) float sm[];
-    uint32_t *sp = reinterpret_cast<uint32_t *>(sm);              // pooled [64][ldp] tf32
-    uint32_t *sa = sp + kStjTcPos * ldp;                           // hidden [64][lda] tf32
-    const int b = blockIdx.y;
-    const bool is_t = (int)blockIdx.x < ntT;
-    const int p0 = (is_t ? blockIdx.x : blockIdx.x - ntT) * kStjTcPos;
-    const int np = min(kStjTcPos, (is_t ? T : V) - p0);
+    float *w1 = sm;                                               // [C/8][WN1][NT1*2 floats][32 lanes] fragments
+    float *w2 = w1 + C * cj;                                      // [cj/8][4][NT2/2 float4][32 lanes]
+    uint32_t *sp = reinterpret_cast<uint32_t *>(w2 + cj * C);     // pooled [64][ldp] tf32
+    uint32_t *sa = sp + kStjTcPos * ldp;                          // hidden [64][lda] tf32
+    float *s_b1 = reinterpret_cast<float *>(sa + kStjTcPos * lda);   // [cj] first-layer bias
+    float *s_b2 = s_b1 + cj;                                      // [C]  second-layer bias
+    float *s_se = s_b2 + C;                                       // [C]  SE gate of the item's clip (frame items)
+    const bool is_t = (int)blockIdx.x < ctasT;
+    const int first = is_t ? blockIdx.x : blockIdx.x - ctasT;
+    const int stride = is_t ? ctasT : (int)gridDim.x - ctasT;
+    const int nitems = is_t ? B * ntT : (B + KC - 1) / KC;
     const float inv = is_t ? 1.0f / (float)V : 1.0f / (float)T;
-    const float *src = is_t ? PT + ((size_t)b * T + p0) * C : PV + ((size_t)b * V + p0) * C;
-    for (int e = threadIdx.x * 4; e < kStjTcPos * C; e += blockDim.x * 4) {
-        const int qq = e / C, c = e - qq * C;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (qq < np) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(seS + (size_t)b * C + c));
-            const float4 v4 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)qq * C + c));
-            x = make_float4(s4.x * (v4.x * inv), s4.y * (v4.y * inv), s4.z * (v4.z * inv), s4.w * (v4.w * inv));
+    {
+        const float4 *g1 = reinterpret_cast<const float4 *>(P1);
+        const float4 *g2 = reinterpret_cast<const float4 *>(is_t ? P2t : P2v);
+        for (int e = threadIdx.x; e < C * cj / 4; e += kStjThreads) {
+            reinterpret_cast<float4 *>(w1)[e] = __ldg(g1 + e);
+            reinterpret_cast<float4 *>(w2)[e] = __ldg(g2 + e);
         }
-        *reinterpret_cast<uint4 *>(sp + qq * ldp + c) = make_uint4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+        const float *bo = is_t ? bt : bv;
+        for (int e = threadIdx.x; e < C; e += kStjThreads) s_b2[e] = bo[e];
+        for (int e = threadIdx.x; e < cj; e += kStjThreads) s_b1[e] = bW[e];
     }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 3, wn = warp >> 2, gr = lane >> 2, tg = lane & 3;
     const int r0 = wm * 16 + gr, r1 = r0 + 8;
-    {   // hidden = hswish(pooled . W + bW): this warp's 16 rows x cj/2 columns
-        constexpr int ncols = cj / 2;
-        const int nb = wn * ncols;
-        float acc[NT1][4];
+    // staging map: float4 e = tid + k*512 -> row e / C4, channels 4*(e % C4) (the same channels for every k)
+    const int srow0 = threadIdx.x / C4, sc = (threadIdx.x % C4) * 4;
+    constexpr int srow_step = kStjThreads / C4;
+
+    // An item is 64 rows.  Frame item: rows = frames p0.. of clip `clip0`.  Joint item: row r = joint r % 17
+    // of clip clip0 + r / 17 (3 clips).  row_src returns the pooled row or nullptr for padding rows.
+    auto decode = [&](int item, int &clip0, int &p0) {
+        if (is_t) {
+            clip0 = item / ntT;
+            p0 = (item - clip0 * ntT) * kStjTcPos;
+        } else {
+            clip0 = item * KC;
+            p0 = 0;
+        }
+    };
+    auto row_index = [&](int clip0, int p0, int row) -> long long {   // row of PT/gT or PV/gV, -1: padding
+        if (is_t) return p0 + row < T ? (long long)clip0 * T + p0 + row : -1;
+        const int q = row / V;
+        return (q < KC && clip0 + q < B) ? (long long)(clip0 + q) * V + (row - q * V) : -1;
+    };
+    float4 pre[NPF], pse[KC];
+    auto prefetch = [&](int item) {
+        int clip0, p0;
+        decode(item, clip0, p0);
 #pragma unroll
-        for (int t = 0; t < NT1; ++t)
+        for (int k = 0; k < NPF; ++k) {
+            const long long ri = row_index(clip0, p0, srow0 + k * srow_step);
+            pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ri >= 0) pre[k] = __ldg(reinterpret_cast<const float4 *>((is_t ? PT : PV) + ri * C + sc));
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
-        const float *pw = P1 + ((size_t)wn * 32 + lane) * (NT1 * 2);
-#pragma unroll 4
-        for (int ks = 0; ks < C / 8; ++ks) {
-            const int k0 = ks * 8;
-            const uint32_t a0 = sp[r0 * ldp + k0 + tg], a1 = sp[r1 * ldp + k0 + tg];
-            const uint32_t a2 = sp[r0 * ldp + k0 + tg + 4], a3 = sp[r1 * ldp + k0 + tg + 4];
-            float bf[NT1 * 2];
-            const float *pk = pw + (size_t)ks * (2 * 32 * NT1 * 2);
-            if constexpr (NT1 == 1) {
-                const float2 v = __ldg(reinterpret_cast<const float2 *>(pk));
-                bf[0] = v.x; bf[1] = v.y;
-            } else {
+        for (int q = 0; q < KC; ++q) {
+            pse[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((q == 0 || !is_t) && clip0 + q < B)
+                pse[q] = __ldg(reinterpret_cast<const float4 *>(seS + (size_t)(clip0 + q) * C + sc));
+        }
+    };
+    if (first < nitems) prefetch(first);
+    for (int item = first; item < nitems; item += stride) {
+        int clip0, p0;
+        decode(item, clip0, p0);
+        // stage the prefetched rows: oracle order (sum / count) scaled by the SE gate, rounded to TF32
 #pragma unroll
-                for (int i = 0; i < NT1 / 2; ++i) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(pk) + i);
-                    bf[4 * i] = v.x; bf[4 * i + 1] = v.y; bf[4 * i + 2] = v.z; bf[4 * i + 3] = v.w;
-                }
+        for (int k = 0; k < NPF; ++k) {
+            const int row = srow0 + k * srow_step;
+            float4 s4 = pse[0];
+            if (!is_t) {
+                const int q = row / V;
+                s4 = q == 0 ? pse[0] : (q == 1 ? pse[1] : pse[2]);
             }
+            const float4 v4 = pre[k];
+            *reinterpret_cast<uint4 *>(sp + row * ldp + sc) =
+                make_uint4(to_tf32(s4.x * (v4.x * inv)), to_tf32(s4.y * (v4.y * inv)), to_tf32(s4.z * (v4.z * inv)),
+                           to_tf32(s4.w * (v4.w * inv)));
+        }
+        if (srow0 == 0) *reinterpret_cast<float4 *>(s_se + sc) = pse[0];
+        __syncthreads();
+        if (item + stride < nitems) prefetch(item + stride);
+        if (wn < WN1) {   // hidden = hswish(pooled . W + bW): this warp's 16 rows x NT1 n-tiles
+            float acc[NT1][4];
 #pragma unroll
             for (int t = 0; t < NT1; ++t)
-                mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
-        }
 #pragma unroll
-        for (int t = 0; t < NT1; ++t) {
-            const int col = nb + t * 8 + 2 * tg;
-            const float b0 = bW[col], b1 = bW[col + 1];
-            sa[r0 * lda + col] = to_tf32(hardswishf(acc[t][0] + b0));
-            sa[r0 * lda + col + 1] = to_tf32(hardswishf(acc[t][1] + b1));
-            sa[r1 * lda + col] = to_tf32(hardswishf(acc[t][2] + b0));
-            sa[r1 * lda + col + 1] = to_tf32(hardswishf(acc[t][3] + b1));
-        }
-    }
-    __syncthreads();
-    const float *P2 = is_t ? P2t : P2v;
-    const float *bo = is_t ? bt : bv;
-    float *dst = is_t ? gT + ((size_t)b * T + p0) * C : gV + ((size_t)b * V + p0) * C;
-    constexpr int ncols2 = C / 2;
-    const int nb2 = wn * ncols2;
+                for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll 4
+            for (int ks = 0; ks < C / 8; ++ks) {
+                const int k0 = ks * 8;
+                const uint32_t a0 = sp[r0 * ldp + k0 + tg], a1 = sp[r1 * ldp + k0 + tg];
+                const uint32_t a2 = sp[r0 * ldp + k0 + tg + 4], a3 = sp[r1 * ldp + k0 + tg + 4];
+                float bf[NT1 * 2];
+                const float *pk = w1 + ((size_t)(ks * WN1 + wn) * 32 + lane) * (NT1 * 2);
+                if constexpr (NT1 == 1) {
+                    const float2 v = *reinterpret_cast<const float2 *>(pk);
+                    bf[0] = v.x; bf[1] = v.y;
+                } else {
+                    const float4 v = *reinterpret_cast<const float4 *>(pk);
+                    bf[0] = v.x; bf[1] = v.y; bf[2] = v.z; bf[3] = v.w;
+                }
 #pragma unroll
-    for (int pass = 0; pass < NPASS; ++pass) {
-        float acc[NT2][4];
-#pragma unroll
-        for (int t = 0; t < NT2; ++t)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
-#pragma unroll 2
-        for (int ks = 0; ks < cj / 8; ++ks) {
-            const int k0 = ks * 8;
-            const uint32_t a0 = sa[r0 * lda + k0 + tg], a1 = sa[r1 * lda + k0 + tg];
-            const uint32_t a2 = sa[r0 * lda + k0 + tg + 4], a3 = sa[r1 * lda + k0 + tg + 4];
-            const float4 *pk = reinterpret_cast<const float4 *>(
-                P2 + ((((size_t)ks * 2 + wn) * NPASS + pass) * 32 + lane) * (NT2 * 2));
-            float bf[NT2 * 2];
-#pragma unroll
-            for (int i = 0; i < NT2 / 2; ++i) {
-                const float4 v = __ldg(pk + i);
-                bf[4 * i] = v.x; bf[4 * i + 1] = v.y; bf[4 * i + 2] = v.z; bf[4 * i + 3] = v.w;
+                for (int t = 0; t < NT1; ++t)
+                    mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
             }
 #pragma unroll
-            for (int t = 0; t < NT2; ++t)
-                mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
+            for (int t = 0; t < NT1; ++t) {
+                const int col = wn * (NT1 * 8) + t * 8 + 2 * tg;
+                const float b0 = s_b1[col], b1 = s_b1[col + 1];
+                *reinterpret_cast<uint2 *>(sa + r0 * lda + col) =
+                    make_uint2(to_tf32(hardswishf(acc[t][0] + b0)), to_tf32(hardswishf(acc[t][1] + b1)));
+                *reinterpret_cast<uint2 *>(sa + r1 * lda + col) =
+                    make_uint2(to_tf32(hardswishf(acc[t][2] + b0)), to_tf32(hardswishf(acc[t][3] + b1)));
+            }
         }
+        __syncthreads();
+        {   // gate = sigmoid(hidden . W2 + b): this warp's 16 rows x C/4 columns
+            float acc[NT2][4];
 #pragma unroll
-        for (int t = 0; t < NT2; ++t) {
-            const int col = nb2 + pass * 64 + t * 8 + 2 * tg;
-            const float2 bc = *reinterpret_cast<const float2 *>(bo + col);
-            float2 s2 = make_float2(1.f, 1.f);
-            if (is_t) s2 = *reinterpret_cast<const float2 *>(seS + (size_t)b * C + col);
-            if (r0 < np)
-                *reinterpret_cast<float2 *>(dst + (size_t)r0 * C + col) =
-                    make_float2(s2.x * sigmoidf_acc(acc[t][0] + bc.x), s2.y * sigmoidf_acc(acc[t][1] + bc.y));
-            if (r1 < np)
-                *reinterpret_cast<float2 *>(dst + (size_t)r1 * C + col) =
-                    make_float2(s2.x * sigmoidf_acc(acc[t][2] + bc.x), s2.y * sigmoidf_acc(acc[t][3] + bc.y));
+            for (int t = 0; t < NT2; ++t)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < cj / 8; ++ks) {
+                const int k0 = ks * 8;
+                const uint32_t a0 = sa[r0 * lda + k0 + tg], a1 = sa[r1 * lda + k0 + tg];
+                const uint32_t a2 = sa[r0 * lda + k0 + tg + 4], a3 = sa[r1 * lda + k0 + tg + 4];
+                const float4 *pk = reinterpret_cast<const float4 *>(w2) + (size_t)(ks * 4 + wn) * (NT2 / 2) * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < NT2 / 2; ++i) {
+                    const float4 v = pk[i * 32];
+                    mma_tf32(acc[2 * i], a0, a1, a2, a3, __float_as_uint(v.x), __float_as_uint(v.y));
+                    mma_tf32(acc[2 * i + 1], a0, a1, a2, a3, __float_as_uint(v.z), __float_as_uint(v.w));
+                }
+            }
+            const long long ri0 = row_index(clip0, p0, r0), ri1 = row_index(clip0, p0, r1);
+            float *dst = is_t ? gT : gV;
+#pragma unroll
+            for (int t = 0; t < NT2; ++t) {
+                const int col = wn * (NT2 * 8) + t * 8 + 2 * tg;
+                const float2 bc = *reinterpret_cast<const float2 *>(s_b2 + col);
+                float2 s2 = make_float2(1.f, 1.f);
+                if (is_t) s2 = *reinterpret_cast<const float2 *>(s_se + col);
+                if (ri0 >= 0)
+                    *reinterpret_cast<float2 *>(dst + ri0 * C + col) =
+                        make_float2(s2.x * sigmoidf_fast(acc[t][0] + bc.x), s2.y * sigmoidf_fast(acc[t][1] + bc.y));
+                if (ri1 >= 0)
+                    *reinterpret_cast<float2 *>(dst + ri1 * C + col) =
+                        make_float2(s2.x * sigmoidf_fast(acc[t][2] + bc.x), s2.y * sigmoidf_fast(acc[t][3] + bc.y));
+            }
         }
+        __syncthreads();   // pooled / hidden / s_se are rewritten by the next item
     }
 }
 
-// Host: re-pack W [K][N] (row-major) into mma.sync m16n8k8 B-fragment order for a warp grid of 2 column
-// halves, `nt` n-tiles per warp and pass:  out[ks][wn][pass][lane][t*2 + h] = W[ks*8 + (lane&3) + 4h][col],
-// col = wn*(N/2) + pass*64 + t*8 + (lane>>2).
-inline void pack_stj_fragments(const float *W, int K, int N, int nt, int npass, std::vector<float> &out) {
+// Host: re-pack W [K][N] (row-major) into mma.sync m16n8k8 B-fragment order for `wn` column groups of
+// N/wn columns (nt = N/wn/8 n-tiles each).  A lane's registers for one k-step are
+//   frag[t*2 + h] = W[ks*8 + (lane&3) + 4h][g*(N/wn) + t*8 + (lane>>2)],  t < nt, h < 2,
+// stored in chunks of `cw` floats (cw = 2 when nt == 1, else 4) with the 32 lanes of a chunk contiguous:
+//   out[(((ks*wn + g) * (2*nt/cw) + chunk) * 32 + lane) * cw + e] = frag[chunk*cw + e]
+// so every warp-wide fragment load is one conflict-free 8- or 16-byte access per lane.
+inline void pack_stj_fragments(const float *W, int K, int N, int wn, std::vector<float> &out) {
+    const int nt = N / wn / 8, cw = nt == 1 ? 2 : 4, nchunk = 2 * nt / cw;
     out.assign((size_t)K * N, 0.f);
-    size_t o = 0;
     for (int ks = 0; ks < K / 8; ++ks)
-        for (int wn = 0; wn < 2; ++wn)
-            for (int pass = 0; pass < npass; ++pass)
-                for (int lane = 0; lane < 32; ++lane)
-                    for (int t = 0; t < nt; ++t)
-                        for (int h = 0; h < 2; ++h) {
-                            const int k = ks * 8 + (lane & 3) + 4 * h;
-                            const int col = wn * (N / 2) + pass * 64 + t * 8 + (lane >> 2);
-                            out[o++] = W[(size_t)k * N + col];
-                        }
+        for (int g = 0; g < wn; ++g)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int t = 0; t < nt; ++t)
+                    for (int h = 0; h < 2; ++h) {
+                        const int f = t * 2 + h, chunk = f / cw, e = f % cw;
+                        const int k = ks * 8 + (lane & 3) + 4 * h;
+                        const int col = g * (N / wn) + t * 8 + (lane >> 2);
+                        out[((((size_t)ks * wn + g) * nchunk + chunk) * 32 + lane) * cw + e] = W[(size_t)k * N + col];
+                    }
 }
 
 // ---- head (README.md:17-18) -----------------------------------------------------------
@@ -576,14 +649,18 @@ int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T,
     }
     if (stj_packed && C == 4 * bp.cj && (C == 64 || C == 128 || C == 256)) {
         const int ntT = cdiv(T, kStjTcPos);
-        dim3 grid(ntT + cdiv(V, kStjTcPos), B);
-        const size_t smem = (size_t)kStjTcPos * ((C + 4) + (bp.cj + 4)) * sizeof(float);
+        const int itemsT = B * ntT, itemsV = cdiv(B, kStjClipsPerJointItem);
+        int grid = std::min(ctx->sm_count, itemsT + itemsV);
+        int ctasV = (int)((double)grid * itemsV / (itemsT + itemsV) + 0.5);
+        ctasV = std::max(1, std::min(ctasV, grid - 1));
+        if (grid < 2) { grid = 2; ctasV = 1; }
+        const size_t smem = C == 64 ? StjCfg<1>::smem_bytes : (C == 128 ? StjCfg<2>::smem_bytes : StjCfg<4>::smem_bytes);
         auto kern = C == 64 ? stj_tc_kernel<V, 1> : (C == 128 ? stj_tc_kernel<V, 2> : stj_tc_kernel<V, 4>);
         if (smem > 48 * 1024) GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             LaunchScope ls(ctx, K_STJ, st, 4.0 * B * (T + V) * C * bp.cj, 2.0 * B * (T + V) * C * 4);
-            kern<<<grid, 256, smem, st>>>(ctx->PT, ctx->PV, ctx->seS, T, ntT, stj_packed[0], bp.jb, stj_packed[1], bp.jbt,
-                                          stj_packed[2], bp.jbv, ctx->gT, ctx->gV);
+            kern<<<grid, kStjThreads, smem, st>>>(ctx->PT, ctx->PV, ctx->seS, B, T, ntT, grid - ctasV, stj_packed[0], bp.jb,
+                                                  stj_packed[1], bp.jbt, stj_packed[2], bp.jbv, ctx->gT, ctx->gV);
         }
         GS_KERNEL_CHECK();
     } else {
