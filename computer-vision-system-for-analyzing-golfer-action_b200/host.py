@@ -250,7 +250,11 @@ class Segmenter:
             raise GolferError(f"B={B},T={T} exceeds the context's max_B={self.max_B},max_T={self.max_T}")
         return B, T
 
-    def segment(self, skel, return_labels: bool = False):
+    def segment(self, skel, return_labels: bool = False, out=None):
+        """skel [B,T,V,C] -> logits [B,T,K] fp32 (and labels [B,T] u8).  Device tensors run on the current
+        stream and return device tensors; host tensors / arrays go through the chunked, copy-overlapped host
+        entry point and return when the result is in host memory.  `out` (host path only): a pinned fp32
+        [B,T,K] tensor to receive the logits instead of a fresh pinned allocation per call."""
         torch = _torch()
         L = self.ctx._L
         K = self.cfg.num_classes
@@ -267,7 +271,13 @@ class Segmenter:
         was_numpy = not isinstance(skel, torch.Tensor)
         x = torch.as_tensor(np.asarray(skel) if was_numpy else skel, dtype=torch.float32).contiguous()
         B, T = self._shape(x.shape)
-        logits = torch.empty((B, T, K), dtype=torch.float32, pin_memory=True)
+        if out is not None:
+            if (not isinstance(out, torch.Tensor) or out.is_cuda or out.dtype != torch.float32
+                    or tuple(out.shape) != (B, T, K) or not out.is_contiguous()):
+                raise GolferError(f"out must be a contiguous host fp32 tensor of shape {(B, T, K)}")
+            logits = out
+        else:
+            logits = torch.empty((B, T, K), dtype=torch.float32, pin_memory=True)
         labels = torch.empty((B, T), dtype=torch.uint8, pin_memory=True) if return_labels else None
         if B and T:
             _check(L.gs_segment_host(self.ctx.handle, x.data_ptr(), logits.data_ptr(),
