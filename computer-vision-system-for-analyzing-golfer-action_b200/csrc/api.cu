@@ -14,7 +14,7 @@ const char *kernel_name(int id) {
     static const char *names[K_COUNT] = {
         "aggregate_fp32", "gemm_gcn_fp32", "gemm_tcn1x1_fp32", "gemm_res_fp32", "tconv_fp32", "stats", "se_gate",
         "stj_gate", "head", "features", "dtw_wavefront", "dtw_generic", "pair_cost", "compare",
-        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc", "dtw_backtrack"};
+        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc", "dtw_backtrack", "normalize_pose"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 
@@ -526,6 +526,23 @@ int gs_compare(gs_ctx *h, const float *a_dev, const float *b_dev, const int32_t 
     GS_CUDA(cudaSetDevice(ctx->device));
     return compare_launch(ctx, a_dev, b_dev, path_dev, path_len_dev, N, Ta, Tb, V, Cc, out_dev,
                           (cudaStream_t)cuda_stream);
+}
+
+int gs_normalize_pose(gs_ctx *h, const float *kp_dev, float *skel_dev, int B, int T, int V, float min_score,
+                      void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx) {
+        set_error("ctx is NULL");
+        return GS_ERR_INVALID;
+    }
+    if (!kp_dev || !skel_dev || B < 0 || T < 1 || V < 13 || !(min_score == min_score)) {
+        set_error("normalize_pose: need kp/skel pointers, B >= 0, T >= 1, V >= 13 (COCO hips are joints 11, 12), "
+                  "a non-NaN min_score; got B=%d T=%d V=%d", B, T, V);
+        return GS_ERR_INVALID;
+    }
+    if (B == 0) return GS_OK;
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return normalize_pose_launch(ctx, kp_dev, skel_dev, B, T, V, min_score, (cudaStream_t)cuda_stream);
 }
 
 int gs_debug_read(gs_ctx *h, const char *name, void *host_out, size_t nbytes) {

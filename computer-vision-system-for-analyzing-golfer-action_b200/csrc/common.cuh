@@ -56,7 +56,7 @@ struct Bf16Path;   // segment_bf16.cu
 enum KernelId {
     K_AGG = 0, K_GEMM_GCN, K_GEMM_TCN1, K_GEMM_RES, K_TCONV, K_STATS, K_SE, K_STJ, K_HEAD, K_FEAT,
     K_DTW, K_DTW_GENERIC, K_PAIRCOST, K_COMPARE,
-    K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC, K_DTW_BACKTRACK,
+    K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC, K_DTW_BACKTRACK, K_POSE,
     K_COUNT
 };
 const char *kernel_name(int id);
@@ -166,6 +166,10 @@ int pair_cost_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, in
                      float *out, cudaStream_t st);
 int compare_launch(Ctx *ctx, const float *a, const float *b, const int32_t *path, const int32_t *plen,
                    int N, int Ta, int Tb, int V, int Cc, float *out, cudaStream_t st);
+
+// pose.cu
+int normalize_pose_launch(Ctx *ctx, const float *kp, float *out, int B, int T, int V, float min_score,
+                          cudaStream_t st);
 
 // segment_fp32.cu
 int segment_fp32_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *labels, int B, int T,

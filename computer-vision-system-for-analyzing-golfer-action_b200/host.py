@@ -32,7 +32,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}
 ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-    "gs_compare", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
+    "gs_compare", "gs_normalize_pose", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
     "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
 
@@ -90,6 +90,7 @@ def load_library():
         L.gs_align_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
         L.gs_pair_cost.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_compare.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+        L.gs_normalize_pose.argtypes = [vp, vp, vp, i32, i32, i32, ctypes.c_float, vp]
         L.gs_launch_count.argtypes = [vp]
         L.gs_launch_count.restype = ctypes.c_int64
         L.gs_workspace_bytes.argtypes = [vp]
@@ -110,7 +111,7 @@ def load_library():
             getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-                     "gs_compare"):
+                     "gs_compare", "gs_normalize_pose"):
             getattr(L, name).restype = ctypes.c_int
         if L.gs_abi_version() != 1:
             raise GolferError("libgolfer_b200.so ABI version mismatch")
@@ -424,3 +425,38 @@ def compare(a, b, path, path_len, ctx: Optional[Context] = None):
                                  path_len.contiguous().data_ptr(), N, Ta, Tb, V, Cc, out.data_ptr(),
                                  _stream_ptr(torch)), "gs_compare")
     return out
+
+
+def normalize_pose(kp, min_score: float = 0.3, ctx: Optional[Context] = None):
+    """Pose-estimation keypoints -> network input (C ABI gs_normalize_pose).
+
+    kp [B,T,V,3] or [T,V,3] = (x, y, score) in image coordinates, COCO-17 joint order.  Returns the
+    hip-centred, torso-scaled skeletons with low-score joints zeroed, same shape, fp32.  Device tensors stay on
+    the device (current stream); host tensors / arrays are copied in and out."""
+    torch = _torch()
+    on_dev = isinstance(kp, torch.Tensor) and kp.is_cuda
+    was_numpy = not isinstance(kp, torch.Tensor)
+    x = kp if on_dev else torch.as_tensor(np.asarray(kp) if was_numpy else kp)
+    x = x.to(torch.float32).contiguous()
+    single = x.dim() == 3
+    if single:
+        x = x.unsqueeze(0)
+    if x.dim() != 4 or x.shape[-1] != 3 or x.shape[2] < 13:
+        raise GolferError(f"normalize_pose expects [B,T,V>=13,3] (x, y, score); got {tuple(kp.shape)}")
+    B, T, V = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    if T < 1:
+        raise GolferError("normalize_pose needs at least one frame")
+    dev = _current_device(torch, x if on_dev else None)
+    ctx = ctx or _align_ctx(dev)
+    xd = x if on_dev else x.to(f"cuda:{dev}")
+    out = torch.empty_like(xd)
+    if B:
+        with torch.cuda.device(dev):
+            _check(ctx._L.gs_normalize_pose(ctx.handle, xd.data_ptr(), out.data_ptr(), B, T, V,
+                                            ctypes.c_float(min_score), _stream_ptr(torch)), "gs_normalize_pose")
+    if single:
+        out = out[0]
+    if on_dev:
+        return out
+    out = out.cpu()
+    return out.numpy() if was_numpy else out

@@ -131,6 +131,17 @@ int gs_compare(gs_ctx *ctx, const float *a_dev, const float *b_dev, const int32_
                const int32_t *path_len_dev, int N, int Ta, int Tb, int V, int Cc,
                float *out_dev, void *cuda_stream);
 
+/* Input adapter from pose estimation (README.md:15): kp_dev [B,T,V,3] fp32 =
+ * (x, y, score) keypoints in image coordinates, COCO-17 joint order (V >= 13) ->
+ * skel_dev [B,T,V,3] fp32 = hip-centred, torso-scaled (x, y) plus the score, the layout
+ * gs_segment consumes.  Frames whose hips score under min_score take the centre of the latest
+ * earlier valid frame (leading frames: the first valid one); the scale is the clip's mean
+ * shoulder-centre to hip-centre distance over frames with all four joints valid (1 if none);
+ * joints scoring under min_score are written as (0,0,0).  Bit-exact vs oracle/pose.py
+ * (individually rounded IEEE fp32 ops, sequential sums).  kp_dev == skel_dev is NOT allowed. */
+int gs_normalize_pose(gs_ctx *ctx, const float *kp_dev, float *skel_dev, int B, int T, int V,
+                      float min_score, void *cuda_stream);
+
 /* Debug hook: copy a named internal device buffer ("X", "XA", "Y", "H", "gcn_trace") to host
  * memory after synchronising the device.  Not part of the product surface. */
 int gs_debug_read(gs_ctx *ctx, const char *name, void *host_out, size_t nbytes);
