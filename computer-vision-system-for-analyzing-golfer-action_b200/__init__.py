@@ -3,7 +3,8 @@
 Public surface (BASELINE.json north_star):
     segment(skel[B,T,V,C]) -> logits[B,T,K]
     align(a, b) -> (cost, path)
-plus the rows SURVEY.md 8f marks next: compare(a, b, path), normalize_pose(keypoints).
+plus the rows SURVEY.md 8f marks next: compare(a, b, path), normalize_pose(keypoints),
+align_phase(a, b, labels_a, labels_b, penalty).
 Everything computes in hand-written sm_100a CUDA kernels behind the C ABI in
 include/golfer_b200.h; there is no CPU fallback.
 """
@@ -13,6 +14,7 @@ from .host import (  # noqa: F401
     GolferError,
     Segmenter,
     align,
+    align_phase,
     compare,
     library_path,
     load_library,

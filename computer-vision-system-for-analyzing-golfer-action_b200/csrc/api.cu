@@ -448,6 +448,31 @@ int gs_align(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, i
     return GS_OK;
 }
 
+int gs_align_phase(gs_ctx *h, const float *a_dev, const float *b_dev, const uint8_t *labels_a_dev,
+                   const uint8_t *labels_b_dev, float penalty, int N, int Ta, int Tb, int V, int Cc,
+                   float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!cost_dev || ((path_dev == nullptr) != (path_len_dev == nullptr))) {
+        set_error("cost_dev must be set; path_dev and path_len_dev must both be set or both NULL");
+        return GS_ERR_INVALID;
+    }
+    if (!labels_a_dev || !labels_b_dev || penalty != penalty) {
+        set_error("align_phase: labels_a / labels_b must be set and penalty must not be NaN");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    GS_CUDA(cudaEventRecord(ctx->ev_start, st));
+    rc = align_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_dev, path_dev, path_len_dev, st, labels_a_dev,
+                      labels_b_dev, penalty);
+    if (rc) return rc;
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
+    ctx->ev_valid = true;
+    return GS_OK;
+}
+
 int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, int Ta, int Tb, int V, int Cc,
                   float *cost_host, int32_t *path_host, int32_t *path_len_host) {
     Ctx *ctx = (Ctx *)h;

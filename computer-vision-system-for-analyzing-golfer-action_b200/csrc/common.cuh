@@ -161,7 +161,8 @@ struct LaunchScope {
 
 // align.cu
 int align_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
-                 float *cost, int32_t *path, int32_t *plen, cudaStream_t st);
+                 float *cost, int32_t *path, int32_t *plen, cudaStream_t st, const uint8_t *la = nullptr,
+                 const uint8_t *lb = nullptr, float penalty = 0.f);
 int pair_cost_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
                      float *out, cudaStream_t st);
 int compare_launch(Ctx *ctx, const float *a, const float *b, const int32_t *path, const int32_t *plen,

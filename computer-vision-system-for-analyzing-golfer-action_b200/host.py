@@ -32,7 +32,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}
 ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-    "gs_compare", "gs_normalize_pose", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
+    "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
     "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
 
@@ -91,6 +91,7 @@ def load_library():
         L.gs_pair_cost.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_compare.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_normalize_pose.argtypes = [vp, vp, vp, i32, i32, i32, ctypes.c_float, vp]
+        L.gs_align_phase.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.gs_launch_count.argtypes = [vp]
         L.gs_launch_count.restype = ctypes.c_int64
         L.gs_workspace_bytes.argtypes = [vp]
@@ -111,7 +112,7 @@ def load_library():
             getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-                     "gs_compare", "gs_normalize_pose"):
+                     "gs_compare", "gs_normalize_pose", "gs_align_phase"):
             getattr(L, name).restype = ctypes.c_int
         if L.gs_abi_version() != 1:
             raise GolferError("libgolfer_b200.so ABI version mismatch")
@@ -460,3 +461,38 @@ def normalize_pose(kp, min_score: float = 0.3, ctx: Optional[Context] = None):
         return out
     out = out.cpu()
     return out.numpy() if was_numpy else out
+
+
+def align_phase(a, b, labels_a, labels_b, penalty: float, ctx: Optional[Context] = None, want_path: bool = True):
+    """Phase-conditioned alignment (C ABI gs_align_phase): `align_batch` with `penalty` added
+    to every cell whose frames carry different phase labels.  Device tensors only (the labels come straight
+    from `Segmenter.segment(..., return_labels=True)`): a [N,Ta,V,Cc], b [N,Tb,V,Cc] fp32, labels_a [N,Ta],
+    labels_b [N,Tb] u8 -> (cost [N], path [N,Ta+Tb-1,2] (-1 padded), path_len [N])."""
+    torch = _torch()
+    for t in (a, b, labels_a, labels_b):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise GolferError("align_phase takes device tensors")
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise GolferError(f"align_phase expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
+    N, Ta, V, Cc = (int(x) for x in a.shape)
+    Tb = int(b.shape[1])
+    if tuple(labels_a.shape) != (N, Ta) or tuple(labels_b.shape) != (N, Tb):
+        raise GolferError(f"labels must be [N,Ta] and [N,Tb]; got {tuple(labels_a.shape)} {tuple(labels_b.shape)}")
+    if Cc < 2 or Ta < 1 or Tb < 1:
+        raise GolferError("align_phase needs (x, y) channels and at least one frame per sequence")
+    la = labels_a.to(torch.uint8).contiguous()
+    lb = labels_b.to(torch.uint8).contiguous()
+    dev = _current_device(torch, a)
+    ctx = ctx or _align_ctx(dev)
+    maxL = Ta + Tb - 1
+    cost = torch.empty((N,), dtype=torch.float32, device=a.device)
+    path = torch.empty((N, maxL, 2), dtype=torch.int32, device=a.device) if want_path else None
+    plen = torch.empty((N,), dtype=torch.int32, device=a.device) if want_path else None
+    if N:
+        _check(ctx._L.gs_align_phase(ctx.handle, a.data_ptr(), b.data_ptr(), la.data_ptr(), lb.data_ptr(),
+                                     ctypes.c_float(penalty), N, Ta, Tb, V, Cc, cost.data_ptr(),
+                                     path.data_ptr() if want_path else None,
+                                     plen.data_ptr() if want_path else None, _stream_ptr(torch)), "gs_align_phase")
+    return cost, path, plen

@@ -114,6 +114,17 @@ int gs_align(gs_ctx *ctx, const float *a_dev, const float *b_dev, int N, int Ta,
              int V, int Cc, float *cost_dev, int32_t *path_dev, int32_t *path_len_dev,
              void *cuda_stream);
 
+/* Phase-conditioned alignment: gs_align with the per-frame phase labels that
+ * gs_segment produced for both clips (labels_a_dev [N,Ta], labels_b_dev [N,Tb] u8, device memory,
+ * so segment -> align needs no host trip).  A cell whose two frames carry different labels costs
+ * `penalty` more:  c'[i,j] = c[i,j] + (labels_a[i] != labels_b[j] ? penalty : 0), one more
+ * individually rounded fp32 add after the division by V; the DTW recurrence, tie-break and outputs
+ * are those of gs_align.  penalty = +inf forbids phase-crossing cells (a path through them costs
+ * inf).  Bit-exact vs oracle/align.py:align_phase_ref. */
+int gs_align_phase(gs_ctx *ctx, const float *a_dev, const float *b_dev, const uint8_t *labels_a_dev,
+                   const uint8_t *labels_b_dev, float penalty, int N, int Ta, int Tb, int V, int Cc,
+                   float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, void *cuda_stream);
+
 /* Same through HOST buffers (copies inside; returns when results are on the host). */
 int gs_align_host(gs_ctx *ctx, const float *a_host, const float *b_host, int N, int Ta,
                   int Tb, int V, int Cc, float *cost_host, int32_t *path_host,

@@ -90,6 +90,22 @@ def align_ref(a: np.ndarray, b: np.ndarray):
     return np.float32(D[-1, -1]), dtw_backtrack(dirs)
 
 
+def phase_cost(c: np.ndarray, la: np.ndarray, lb: np.ndarray, penalty: float) -> np.ndarray:
+    """Phase-conditioned cost: c'[i,j] = c[i,j] + (la[i] != lb[j] ? penalty : 0),
+    one rounded fp32 add on top of pair_cost.  la [Ta], lb [Tb] integer phase labels."""
+    c = np.asarray(c, dtype=np.float32)
+    pen = np.where(np.asarray(la)[:, None] != np.asarray(lb)[None, :], np.float32(penalty), np.float32(0))
+    with np.errstate(invalid="ignore", over="ignore"):
+        return (c + pen.astype(np.float32)).astype(np.float32)
+
+
+def align_phase_ref(a: np.ndarray, b: np.ndarray, la: np.ndarray, lb: np.ndarray, penalty: float):
+    """One pair with phase labels: (cost fp32 scalar, path [L,2] int32)."""
+    c = phase_cost(pair_cost(a, b), la, lb, penalty)
+    D, dirs = dtw_accumulate(c)
+    return np.float32(D[-1, -1]), dtw_backtrack(dirs)
+
+
 def dtw_bruteforce(c: np.ndarray) -> float:
     """Minimum path cost by exhaustive enumeration (tiny Ta,Tb only); float64 sums,
     used by the oracle's own known-answer tests."""

@@ -93,6 +93,29 @@ float oracle_dtw(const float *c, int Ta, int Tb, int32_t *path, int32_t *path_le
     return total;
 }
 
+/* oracle/align.py:align_phase_ref over a batch: la [N,Ta], lb [N,Tb] phase labels, one more rounded
+ * add per cell: c' = c + (la[i] != lb[j] ? penalty : 0).  la == NULL: plain align_ref. */
+void oracle_align_phase_batch(const float *a, const float *b, const uint8_t *la, const uint8_t *lb,
+                              float penalty, int N, int Ta, int Tb, int V, int Cc, float *cost,
+                              int32_t *path, int32_t *path_len, int num_threads)
+{
+    int maxL = Ta + Tb - 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads)
+    for (int n = 0; n < N; ++n) {
+        float *c = (float *)malloc(sizeof(float) * (size_t)Ta * Tb);
+        oracle_pair_cost(a + (size_t)n * Ta * V * Cc, b + (size_t)n * Tb * V * Cc, Ta, Tb, V, Cc, c);
+        if (la) {
+            for (int i = 0; i < Ta; ++i)
+                for (int j = 0; j < Tb; ++j) {
+                    float pen = la[(size_t)n * Ta + i] != lb[(size_t)n * Tb + j] ? penalty : 0.0f;
+                    c[(size_t)i * Tb + j] = c[(size_t)i * Tb + j] + pen;
+                }
+        }
+        cost[n] = oracle_dtw(c, Ta, Tb, path + (size_t)n * maxL * 2, path_len + n, NULL, NULL);
+        free(c);
+    }
+}
+
 /* oracle/align.py:align_ref over a batch. a [N,Ta,V,Cc], b [N,Tb,V,Cc];
  * cost [N], path [N,Ta+Tb-1,2] (-1 padded), path_len [N].  Pairs are
  * independent, so the OpenMP loop does not change any result. */

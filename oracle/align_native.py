@@ -24,6 +24,10 @@ def lib():
         L.oracle_pair_cost.restype = None
         L.oracle_align_batch.argtypes = [fp, fp] + [ctypes.c_int] * 5 + [fp, ip, ip, ctypes.c_int]
         L.oracle_align_batch.restype = None
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.oracle_align_phase_batch.argtypes = ([fp, fp, u8p, u8p, ctypes.c_float] + [ctypes.c_int] * 5 +
+                                               [fp, ip, ip, ctypes.c_int])
+        L.oracle_align_phase_batch.restype = None
         _lib = L
     return _lib
 
@@ -57,4 +61,23 @@ def align_batch_c(a, b, num_threads: int = 1):
     plen = np.empty(N, dtype=np.int32)
     lib().oracle_align_batch(_fp(a), _fp(b), N, Ta, Tb, V, Cc, _fp(cost), _ip(path), _ip(plen),
                              int(num_threads))
+    return cost, path, plen
+
+
+def align_phase_batch_c(a, b, la, lb, penalty: float, num_threads: int = 1):
+    """align_batch_c with phase labels la [N,Ta], lb [N,Tb] (u8) and the mismatch penalty."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    la = np.ascontiguousarray(la, dtype=np.uint8)
+    lb = np.ascontiguousarray(lb, dtype=np.uint8)
+    N, Ta, V, Cc = a.shape
+    Tb = b.shape[1]
+    assert la.shape == (N, Ta) and lb.shape == (N, Tb)
+    cost = np.empty(N, dtype=np.float32)
+    path = np.empty((N, Ta + Tb - 1, 2), dtype=np.int32)
+    plen = np.empty(N, dtype=np.int32)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    lib().oracle_align_phase_batch(_fp(a), _fp(b), la.ctypes.data_as(u8p), lb.ctypes.data_as(u8p),
+                                   ctypes.c_float(penalty), N, Ta, Tb, V, Cc, _fp(cost), _ip(path), _ip(plen),
+                                   int(num_threads))
     return cost, path, plen

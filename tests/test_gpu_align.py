@@ -146,3 +146,58 @@ def test_bad_arguments_raise():
         golfer_b200.host.align_batch(a, torch.zeros(3, 8, 17, 2, device="cuda"))
     with pytest.raises(golfer_b200.GolferError):
         golfer_b200.host.align_batch(a[..., :1], a[..., :1])
+
+
+# ---- phase-conditioned alignment ------------------------------------------------
+def _phase_labels(N, T, seed, nphase=5):
+    """Monotone phase labels with random run lengths (what a segmentation of a swing looks like)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((N, T), np.uint8)
+    for n in range(N):
+        cuts = np.sort(rng.integers(0, T + 1, nphase - 1))
+        out[n] = np.searchsorted(cuts, np.arange(T), side="right")
+    return out
+
+
+@pytest.mark.parametrize("N,Ta,Tb,pen", [(6, 300, 300, 0.5), (5, 300, 257, 2.0), (4, 64, 300, 0.5), (3, 1, 1, 1.0),
+                                         (4, 33, 1, 1.0), (5, 300, 300, float("inf")), (4, 120, 90, 0.0),
+                                         (700, 40, 40, 0.75)])
+def test_phase_alignment_matches_oracle_bitwise(N, Ta, Tb, pen):
+    a, b = oalign.synth_swings(N, Ta, Tb, seed=Ta * 5 + Tb)
+    la, lb = _phase_labels(N, Ta, 1), _phase_labels(N, Tb, 2)
+    ref_cost, ref_path, ref_plen = align_native.align_phase_batch_c(a, b, la, lb, pen, 4)
+    cost, path, plen = golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(lb), pen)
+    assert np.array_equal(cost.cpu().numpy(), ref_cost)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+    cost_only, _, _ = golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(lb), pen, want_path=False)
+    assert np.array_equal(cost_only.cpu().numpy(), ref_cost)
+
+
+def test_segment_labels_feed_phase_alignment_on_device():
+    # segment -> labels -> align_phase without a host trip; checked against the oracle run on the
+    # labels the GPU produced (label parity itself is tests/test_gpu_segment.py's subject)
+    cfg = golfer_b200.V0
+    seg = golfer_b200.Segmenter(cfg, seed=1234, precision="bf16", max_B=8, max_T=96)
+    from oracle import segnet as osegnet
+    skel = torch.from_numpy(osegnet.synth_skeletons(8, 96, cfg, seed=4)).cuda()
+    _, labels = seg.segment(skel, return_labels=True)
+    a, b = skel[0::2, :, :, :2].contiguous(), skel[1::2, :, :, :2].contiguous()
+    la, lb = labels[0::2].contiguous(), labels[1::2].contiguous()
+    cost, path, plen = golfer_b200.align_phase(a, b, la, lb, 0.5)
+    rc, rp, rl = align_native.align_phase_batch_c(a.cpu().numpy(), b.cpu().numpy(), la.cpu().numpy(),
+                                                  lb.cpu().numpy(), 0.5, 2)
+    assert np.array_equal(cost.cpu().numpy(), rc) and np.array_equal(path.cpu().numpy(), rp)
+    assert np.array_equal(plen.cpu().numpy(), rl)
+    seg.ctx.close()
+
+
+def test_phase_alignment_rejects_bad_arguments():
+    a, b = oalign.synth_swings(2, 10, 10, seed=1)
+    la = np.zeros((2, 10), np.uint8)
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(la[:, :5]), 1.0)
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.align_phase(a, b, la, la, 1.0)                      # host arrays
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(la), float("nan"))

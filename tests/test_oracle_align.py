@@ -143,3 +143,36 @@ def test_compare_ref_matches_cost_terms():
         for v in range(17):
             acc = np.float32(acc + d[l, v])
         assert np.float32(acc / np.float32(17)) == c[i, j]
+
+
+# ---- phase-conditioned alignment -------------------------------------------
+def test_phase_penalty_zero_is_plain_alignment_and_c_matches_numpy():
+    a, b = align.synth_swings(3, 23, 19, seed=5)
+    rng = np.random.default_rng(0)
+    la = rng.integers(0, 4, (3, 23)).astype(np.uint8)
+    lb = rng.integers(0, 4, (3, 19)).astype(np.uint8)
+    c0, p0, l0 = align_native.align_batch_c(a, b)
+    c1, p1, l1 = align_native.align_phase_batch_c(a, b, la, lb, 0.0)
+    assert np.array_equal(c0, c1) and np.array_equal(p0, p1) and np.array_equal(l0, l1)
+    for pen in (0.25, 3.0, np.inf):
+        cc, pc, lc = align_native.align_phase_batch_c(a, b, la, lb, pen)
+        for n in range(3):
+            cost, path = align.align_phase_ref(a[n], b[n], la[n], lb[n], pen)
+            assert cost == cc[n] or (np.isinf(cost) and np.isinf(cc[n]))
+            assert lc[n] == len(path) and np.array_equal(pc[n, :len(path)], path)
+
+
+def test_phase_penalty_keeps_the_path_inside_matching_phases():
+    # two clips with the same three phases but different durations: with a large penalty the path
+    # only visits cells whose labels agree (such a path exists: the phase order is the same)
+    la = np.repeat(np.uint8([0, 1, 2]), [6, 10, 4])
+    lb = np.repeat(np.uint8([0, 1, 2]), [9, 3, 8])
+    a, _ = align.synth_swings(1, 20, 20, seed=11)
+    _, b = align.synth_swings(1, 20, 20, seed=12)
+    cost, path = align.align_phase_ref(a[0], b[0], la, lb, 1e6)
+    assert np.all(la[path[:, 0]] == lb[path[:, 1]])
+    assert cost < 1e6
+    plain_cost, plain_path = align.align_ref(a[0], b[0])
+    assert cost >= plain_cost
+    # the unconstrained optimum crosses phases here, so the constraint really binds
+    assert np.any(la[plain_path[:, 0]] != lb[plain_path[:, 1]])
