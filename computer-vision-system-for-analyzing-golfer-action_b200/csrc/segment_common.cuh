@@ -516,6 +516,19 @@ constexpr int kHeadFrames = 32;
 
 template <typename TU> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> {
+    typedef uint4 Raw;     // 8 channels as loaded: kept packed in registers until they are used
+    static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16 *p) {
+        return __ldg(reinterpret_cast<const uint4 *>(p));
+    }
+    static __device__ __forceinline__ void unpack(const Raw &r, float (&f)[8]) {
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 t = __bfloat1622float2(h[e]);
+            f[2 * e] = t.x;
+            f[2 * e + 1] = t.y;
+        }
+    }
     static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) {
         const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
         const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&r);
@@ -528,6 +541,16 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 template <> struct Vec8<float> {
+    struct Raw { float4 a, d; };
+    static __device__ __forceinline__ Raw load_raw(const float *p) {
+        Raw r;
+        r.a = __ldg(reinterpret_cast<const float4 *>(p));
+        r.d = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw &r, float (&f)[8]) {
+        f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.d.x; f[5] = r.d.y; f[6] = r.d.z; f[7] = r.d.w;
+    }
     static __device__ __forceinline__ void load(const float *p, float (&f)[8]) {
         const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
         const float4 d = __ldg(reinterpret_cast<const float4 *>(p) + 1);
@@ -535,6 +558,7 @@ template <> struct Vec8<float> {
     }
 };
 
+// Generic form (any C % 8 == 0, K <= 32; the fp32 parity path): loads as the compiler schedules them.
 // A warp owns 4 frames: lane = (frame f = lane / 8, channel group g = lane % 8); a lane walks the 8-channel
 // vectors g, g+8, ... of its frame, folds them straight into K logit partials, and the partials are reduced
 // over the 8 lanes of the frame (3 shuffle steps for 4 frames at once).  kHeadFrames = 32 frames per CTA.
@@ -591,6 +615,109 @@ head_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const float 
     int arg = 0;
 #pragma unroll
     for (int k = 0; k < 32; ++k)
+        if (k < K) {
+            float x = part[k];
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            x += bh[k];
+            if (g == 0 && tv) logits[bt * K + k] = x;
+            if (k == 0 || x > best) { best = x; arg = k; }      // first arg-max: ties -> lowest class index
+        }
+    if (labels && g == 0 && tv) labels[bt] = (uint8_t)arg;
+}
+
+// Streaming form (bf16 path, C % 64 == 0, K <= 16).
+// A warp owns 4 frames: lane = (frame f = lane / 8, channel group g = lane % 8); a lane walks the 8-channel
+// vectors g, g+8, ... of its frame, folds them straight into K logit partials, and the partials are reduced
+// over the 8 lanes of the frame (3 shuffle steps for 4 frames at once).  kHeadFrames = 32 frames per CTA.
+// The launch is HBM-bound (one pass over U), so what matters is bytes in flight: the 17 joint vectors of
+// an 8-channel group are loaded as one batch of 16-byte loads before any of them is used (the 80-register
+// build issued them 4-5 at a time: 3.3 TB/s), and the gate / weight rows sit in shared memory in a
+// lane-interleaved order so that the 8 lanes of a frame read 128 contiguous bytes per LDS.128
+// (channel c of a 64-channel group lives at float (c%8/4)*32 + (c/8)*4 + c%4; the plain order was a
+// 2-way bank conflict on every gate load).
+constexpr int kHeadMaxK = 16;
+
+__device__ __forceinline__ int head_perm(int c) {    // position of channel c inside its 64-channel group
+    const int w = c & 63;
+    return (c & ~63) + ((w & 7) >> 2) * 32 + (w >> 3) * 4 + (w & 3);
+}
+
+template <typename TU, int V>
+__global__ void __launch_bounds__(256, 2)
+head_stream_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const float *__restrict__ gV, int T, int C,
+                   int K, const float *__restrict__ WhT, const float *__restrict__ bh, float *__restrict__ logits,
+                   uint8_t *__restrict__ labels) {
+    extern __shared__ __align__(16) float sm[];     // gV[b]: [V][C], then WhT: [K][C], both lane-interleaved
+    float *sgv = sm, *swh = sm + V * C;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = lane >> 3, g = lane & 7;
+    const int t = blockIdx.x * kHeadFrames + warp * 4 + f;
+    const bool tv = t < T;
+    const size_t bt = (size_t)b * T + (tv ? t : T - 1);
+    const TU *row = U + (bt * V) * C + g * 8;
+    const float *gtrow = gT + bt * C + g * 8;
+    // the first batch of activation loads goes out before the gate / weight rows are staged, so HBM is
+    // busy while this CTA fills its shared memory
+    typename Vec8<float>::Raw gtr = Vec8<float>::load_raw(gtrow);
+    typename Vec8<TU>::Raw xr[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) xr[v] = Vec8<TU>::load_raw(row + (size_t)v * C);
+    for (int e = threadIdx.x * 4; e < V * C; e += blockDim.x * 4) {
+        const int r = e / C, c = e - r * C;
+        *reinterpret_cast<float4 *>(sgv + r * C + head_perm(c)) =
+            __ldg(reinterpret_cast<const float4 *>(gV + (size_t)b * V * C + e));
+    }
+    for (int e = threadIdx.x * 4; e < K * C; e += blockDim.x * 4) {
+        const int r = e / C, c = e - r * C;
+        *reinterpret_cast<float4 *>(swh + r * C + head_perm(c)) = __ldg(reinterpret_cast<const float4 *>(WhT + e));
+    }
+    __syncthreads();
+    float part[kHeadMaxK];
+#pragma unroll
+    for (int k = 0; k < kHeadMaxK; ++k) part[k] = 0.f;
+    for (int cg = 0; cg < C; cg += 64) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const float *gbase = sgv + cg + g * 4;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 g0 = *reinterpret_cast<const float4 *>(gbase + v * C);
+            const float4 g1 = *reinterpret_cast<const float4 *>(gbase + v * C + 32);
+            float x[8];
+            Vec8<TU>::unpack(xr[v], x);
+            acc[0] += x[0] * g0.x; acc[1] += x[1] * g0.y; acc[2] += x[2] * g0.z; acc[3] += x[3] * g0.w;
+            acc[4] += x[4] * g1.x; acc[5] += x[5] * g1.y; acc[6] += x[6] * g1.z; acc[7] += x[7] * g1.w;
+        }
+        {
+            float gt[8];
+            Vec8<float>::unpack(gtr, gt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = acc[e] * gt[e] * (1.0f / (float)V);
+        }
+        if (cg + 64 < C) {                       // next batch in flight while the logit partials are folded
+            gtr = Vec8<float>::load_raw(gtrow + cg + 64);
+#pragma unroll
+            for (int v = 0; v < V; ++v) xr[v] = Vec8<TU>::load_raw(row + (size_t)v * C + cg + 64);
+        }
+        const float *wbase = swh + cg + g * 4;
+#pragma unroll
+        for (int k = 0; k < kHeadMaxK; ++k)
+            if (k < K) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wbase + k * C);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wbase + k * C + 32);
+                part[k] += acc[0] * w0.x + acc[1] * w0.y + acc[2] * w0.z + acc[3] * w0.w + acc[4] * w1.x +
+                           acc[5] * w1.y + acc[6] * w1.z + acc[7] * w1.w;
+            }
+    }
+    // reduce over the 8 channel-group lanes of each frame; lane g == 0 of a frame ends with the totals
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < kHeadMaxK; ++k)
         if (k < K) {
             float x = part[k];
             x += __shfl_xor_sync(0xffffffffu, x, 4);
@@ -684,6 +811,18 @@ int launch_head(Ctx *ctx, const TU *U, int B, int T, int C, float *logits, uint8
     constexpr int V = 17;
     const int K = ctx->cfg.num_classes;
     const size_t smem = (size_t)(V + K) * C * sizeof(float);
+    if (sizeof(TU) == 2 && K <= kHeadMaxK && C % 64 == 0) {
+        if (smem > 48 * 1024)
+            GS_CUDA(cudaFuncSetAttribute(head_stream_kernel<TU, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            LaunchScope ls(ctx, K_HEAD, st, 2.0 * B * T * C * (V + K), (double)B * T * V * C * sizeof(TU));
+            dim3 grid(cdiv(T, kHeadFrames), B);
+            head_stream_kernel<TU, V><<<grid, 256, smem, st>>>(U, ctx->gT, ctx->gV, T, C, K, ctx->headWT, ctx->headb,
+                                                               logits, labels);
+        }
+        GS_KERNEL_CHECK();
+        return GS_OK;
+    }
     if (smem > 48 * 1024)
         GS_CUDA(cudaFuncSetAttribute(head_kernel<TU, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
