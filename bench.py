@@ -464,6 +464,10 @@ def main():
         "frac_of_hbm_peak": cfg.compulsory_bytes_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e9 / peaks["hbm"],
     }
 
+    # SM clock for the instruction-pipe peaks below: the device's maximum (the sampled clock is reported
+    # beside it in `clocks`; a run that did not hold it is rejected anyway)
+    clocks_hint_mhz = torch.cuda.get_device_properties(local).clock_rate / 1000.0
+
     # ---- alignment: 4096 pairs of 300x300 per GPU ------------------------------------
     align_obj = None
     if not args.no_align:
@@ -519,10 +523,61 @@ def main():
                     "d2h_bytes_per_step": int(N * (maxL * 8 + 8))},
             "roofline": {"kernel": "dtw_wavefront", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
-                         "note": "compulsory bytes 86,396 B/pair; the binding limit is fp32 issue/sqrt "
-                                 "throughput (~1.5-3 M pairs/s per GPU), not HBM (SURVEY.md 7 item 4)",
-                         "instr_bound_pairs_per_s_per_gpu": 1.5e6},
+                         "note": "compulsory bytes 86,396 B/pair: HBM is not the binding limit (SURVEY.md 7 item 4); "
+                                 "see fp32_pipe"},
         }
+        # The binding resource: every cell costs 17 joints x 10 individually rounded fp32 ops (the bit-exact
+        # contract forbids fusing them) + ~10 for the division and the DP step = 180 lane-ops on the FMA
+        # pipe (128 lanes/clk/SM; packed f32x2 instructions halve the issue slots, not the lane-cycles:
+        # experiments/f32x2_probe.cu) and 18 MUFU ops (16 lanes/clk/SM).
+        if aprof and clocks_hint_mhz:
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            cells = float(N) * T_FRAMES * T_FRAMES
+            lane_ops = 180.0 * cells * aprof["launches"]
+            fma_peak = 128.0 * sms * clocks_hint_mhz * 1e6
+            mufu_peak = 16.0 * sms * clocks_hint_mhz * 1e6
+            t = aprof["ms"] * 1e-3
+            align_obj["fp32_pipe"] = {
+                "bound": "fp32 FMA pipe", "lane_ops_per_cell": 180, "achieved_lane_ops_per_s": lane_ops / t,
+                "peak_lane_ops_per_s": fma_peak, "frac": lane_ops / t / fma_peak,
+                "mufu_frac": 18.0 * cells * aprof["launches"] / t / mufu_peak,
+                "pairs_per_s_at_peak": fma_peak / (180.0 * T_FRAMES * T_FRAMES),
+                "sm_mhz_assumed": clocks_hint_mhz}
+            bt = actx.profile_read().get("dtw_backtrack")
+            if bt:
+                align_obj["kernels"] = {"dtw_wavefront_ms": aprof["ms"] / aprof["launches"],
+                                        "dtw_backtrack_ms": bt["ms"] / bt["launches"]}
+
+    # ---- the rows SURVEY.md 8f marks next: pose adapter, phase-conditioned alignment ------------
+    extras = {}
+    if not args.no_align and args.workload == "segment":
+        kp = torch.rand(B, T_FRAMES, 17, 3, device=dev) * 400.0
+        ectx = golfer_b200.host.Context(local)
+        for _ in range(W):
+            golfer_b200.normalize_pose(kp, 0.3, ctx=ectx)
+        e0.record()
+        for _ in range(K):
+            golfer_b200.normalize_pose(kp, 0.3, ctx=ectx)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        nbytes = 2.0 * kp.numel() * 4
+        extras["normalize_pose"] = {"ms": ms, "clips_per_s": B / (ms * 1e-3), "bound": "hbm",
+                                    "achieved_gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peaks["hbm"],
+                                    "note": f"{B} clips x {T_FRAMES} frames: {nbytes / 1e6:.1f} MB per launch, "
+                                            "launch-latency sized"}
+        la = (torch.arange(T_FRAMES, device=dev) * 8 // T_FRAMES).to(torch.uint8).expand(N, T_FRAMES).contiguous()
+        for _ in range(W):
+            golfer_b200.align_phase(a, b, la, la, 0.5, ctx=actx)
+        e0.record()
+        for _ in range(K):
+            golfer_b200.align_phase(a, b, la, la, 0.5, ctx=actx)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        extras["align_phase"] = {"ms": ms, "pairs_per_s": N / (ms * 1e-3),
+                                 "note": "gs_align_phase, same 4096 pairs, 8 equal phases, penalty 0.5"}
+        ectx.close()
 
     clocks = sampler.stop() if rank == 0 else None   # covers every timed region above
 
@@ -552,6 +607,7 @@ def main():
                        "collective": "all_gather(logits) inside each step" if world > 1 else "none"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "whole_net": whole_net, "kernels": kernels, "cpu_baseline": cpu_baseline, "align": align_obj,
+            "extras": extras or None,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
