@@ -410,27 +410,36 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 if (prm.gT) {
                     const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][64]
                     const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][64]
+                    // thread = (16-byte chunk cc, rows r = rbase + 16k): the swizzled chunk position
+                    // cc ^ (r & 7) does not depend on k, and (frame, joint) of the row advance by
+                    // (0, +16) with one carry, so the loop body has no division and no swizzle math
+                    const int cc = gt_id & 7, rbase = gt_id >> 3;
+                    unsigned char *sp0 = sl + (size_t)rbase * 128 + ((cc ^ (rbase & 7)) << 4);
+                    int f = 0, v = rbase;                                  // rbase < 16 < 17
+                    const int rows_left = prm.rows_per_clip - row0;       // rows >= this are TMA zero fill
 #pragma unroll 4
-                    for (int idx = gt_id; idx < kTileM * 8; idx += kGateThreads) {
-                        const int r = idx >> 3, cc = idx & 7;
-                        if (row0 + r >= prm.rows_per_clip) continue;     // TMA zero-filled rows
-                        const int f = r / 17, v = r - f * 17;
-                        uint4 *sp = reinterpret_cast<uint4 *>(sl + (size_t)r * 128 + ((cc ^ (r & 7)) << 4));
-                        const uint4 x = *sp;
-                        const float4 t0 = sgt[f * 16 + cc * 2], t1 = sgt[f * 16 + cc * 2 + 1];
-                        const float4 v0 = sgv[v * 16 + cc * 2], v1 = sgv[v * 16 + cc * 2 + 1];
-                        const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
-                        // (x * gT) * gV, same rounding order as the scalar form, two products per FMUL2
-                        const float2 a = fmul2(fmul2(__bfloat1622float2(xp[0]), make_float2(t0.x, t0.y)), make_float2(v0.x, v0.y));
-                        const float2 c2 = fmul2(fmul2(__bfloat1622float2(xp[1]), make_float2(t0.z, t0.w)), make_float2(v0.z, v0.w));
-                        const float2 d = fmul2(fmul2(__bfloat1622float2(xp[2]), make_float2(t1.x, t1.y)), make_float2(v1.x, v1.y));
-                        const float2 e = fmul2(fmul2(__bfloat1622float2(xp[3]), make_float2(t1.z, t1.w)), make_float2(v1.z, v1.w));
-                        uint4 o;
-                        o.x = pack_bf16(a.x, a.y);
-                        o.y = pack_bf16(c2.x, c2.y);
-                        o.z = pack_bf16(d.x, d.y);
-                        o.w = pack_bf16(e.x, e.y);
-                        *sp = o;
+                    for (int k = 0; k < kTileM / 16; ++k) {
+                        const int r = rbase + 16 * k;
+                        if (r < rows_left) {
+                            uint4 *sp = reinterpret_cast<uint4 *>(sp0 + (size_t)k * 2048);
+                            const uint4 x = *sp;
+                            const float4 t0 = sgt[f * 16 + cc * 2], t1 = sgt[f * 16 + cc * 2 + 1];
+                            const float4 v0 = sgv[v * 16 + cc * 2], v1 = sgv[v * 16 + cc * 2 + 1];
+                            const __nv_bfloat162 *xp = reinterpret_cast<const __nv_bfloat162 *>(&x);
+                            // (x * gT) * gV, same rounding order as the scalar form, two products per FMUL2
+                            const float2 a = fmul2(fmul2(__bfloat1622float2(xp[0]), make_float2(t0.x, t0.y)), make_float2(v0.x, v0.y));
+                            const float2 c2 = fmul2(fmul2(__bfloat1622float2(xp[1]), make_float2(t0.z, t0.w)), make_float2(v0.z, v0.w));
+                            const float2 d = fmul2(fmul2(__bfloat1622float2(xp[2]), make_float2(t1.x, t1.y)), make_float2(v1.x, v1.y));
+                            const float2 e = fmul2(fmul2(__bfloat1622float2(xp[3]), make_float2(t1.z, t1.w)), make_float2(v1.z, v1.w));
+                            uint4 o;
+                            o.x = pack_bf16(a.x, a.y);
+                            o.y = pack_bf16(c2.x, c2.y);
+                            o.z = pack_bf16(d.x, d.y);
+                            o.w = pack_bf16(e.x, e.y);
+                            *sp = o;
+                        }
+                        v += 16;
+                        if (v >= 17) { v -= 17; ++f; }
                     }
                     fence_proxy_async_smem();
                 }
