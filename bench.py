@@ -66,6 +66,9 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------ clocks ------
+E2E_REPEATS = 3
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled while the timed regions run.  In-process NVML (nvidia_ml_py)
     on a thread: an `nvidia-smi -lms` child process stalls the host-synchronous e2e calls for tens of
@@ -415,16 +418,24 @@ def main():
     for _ in range(W):
         seg.segment(skel_host)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        out_host = seg.segment(skel_host)           # H2D + kernels + D2H, returns when done
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    # The loop is host-synchronous, so a descheduled host thread on a shared box shows up one-for-one
+    # (single runs of K = 10 steps ranged 35-46 k clips/s): K steps are timed E2E_REPEATS times and
+    # the fastest repetition is reported, with all repetitions listed beside it.
+    e2e_runs = []
+    for _ in range(E2E_REPEATS):
+        t0 = time.perf_counter()
+        for _ in range(K):
+            out_host = seg.segment(skel_host)           # H2D + kernels + D2H, returns when done
+        torch.cuda.synchronize()
+        e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
+        barrier()
+    e2e_s = min(e2e_runs)
     if rank == 0:
         sampler.resume()
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(skel_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)}
+           "h2d_bytes_per_step": int(skel_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+           "policy": f"fastest of {E2E_REPEATS} repetitions of {K} steps",
+           "all_repetitions": [world * B * K / t for t in e2e_runs]}
 
     # ---- dominant kernel -> roofline --------------------------------------------
     roofline = None
@@ -505,12 +516,15 @@ def main():
         for _ in range(W):          # the host entry point grows its staging buffers on first use
             golfer_b200.host.align_batch(a_host, b_host, ctx=actx)
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            golfer_b200.host.align_batch(a_host, b_host, ctx=actx)
-        torch.cuda.synchronize()
-        al_e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
+        al_runs = []
+        for _ in range(E2E_REPEATS):
+            t0 = time.perf_counter()
+            for _ in range(K):
+                golfer_b200.host.align_batch(a_host, b_host, ctx=actx)
+            torch.cuda.synchronize()
+            al_runs.append(max_over_ranks(time.perf_counter() - t0))
+            barrier()
+        al_e2e_s = min(al_runs)
         if rank == 0:
             sampler.resume()
         pairs_s = world * N * K / (al_ms * 1e-3)
@@ -520,7 +534,9 @@ def main():
             "ms_per_step": al_ms / K, "pairs_per_step_per_gpu": N,
             "e2e": {"value": world * N * K / al_e2e_s, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(a_host.numel() * 4 * 2),
-                    "d2h_bytes_per_step": int(N * (maxL * 8 + 8))},
+                    "d2h_bytes_per_step": int(N * (maxL * 8 + 8)),
+                    "policy": f"fastest of {E2E_REPEATS} repetitions of {K} steps",
+                    "all_repetitions": [world * N * K / t for t in al_runs]},
             "roofline": {"kernel": "dtw_wavefront", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
                          "note": "compulsory bytes 86,396 B/pair: HBM is not the binding limit (SURVEY.md 7 item 4); "

@@ -32,6 +32,7 @@ struct Bf16Path {
     std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
     std::vector<float *> bias_t;                        // b2 (+ br)
     std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in TF32 fragment order (stj_tc_kernel)
+    float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
     std::vector<BlockMaps> maps;
     int maps_T = -1;
     bool stj_tc = true;         // GOLFER_STJ_FFMA=1 keeps the exact-fp32 FFMA ST-joint kernel
@@ -150,6 +151,154 @@ front_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale,
         const size_t o = (f0 * V17 + row) * C + c0;
         *reinterpret_cast<uint2 *>(Y + o) = py;
         *reinterpret_cast<uint2 *>(R0 + o) = pr;
+    }
+}
+
+// ---- block 0 with the two K = 9 / K = 3 mixes on warp-level tensor cores ---------------------------
+// The CUDA-core form above is bound by FMA issue (12 x 2C FMAs per row; 0.15 ms against a 0.054 ms
+// write floor).  Here a row's inputs form one 16-wide A row
+//     [ 9 aggregated inputs | 3 normalised raw inputs | 1 | 0 0 0 ]
+// and BOTH outputs come from one [16 x 2C] matrix (host: pack_front_matrix)
+//     columns [0,C)  : rows 0-8 = Wg, row 12 = bg          -> Y  = relu(.)
+//     columns [C,2C) : rows 9-11 = Wr, row 12 = br         -> R0 (the block's residual projection)
+// as mma.sync m16n8k8 TF32 with fp32 accumulation (inputs and weights rounded to TF32: 2^-11, below the
+// bf16 rounding of the outputs).  One CTA = kFrontFrames frames = 17 m-tiles of 16 rows; a warp owns a
+// 32-column group (its 16 B-fragment registers never change) and every (8 / groups)-th m-tile.
+constexpr int kFrontLd = 20;     // A-row stride in floats: conflict-free fragment loads
+
+// 4x4 transpose of 32-bit values across the 4 lanes of a quad (lane q holds row q on entry, column q on exit)
+__device__ __forceinline__ void quad_transpose(uint32_t (&p)[4], int q) {
+    const bool odd = q & 1, hi = q & 2;
+    uint32_t s0 = odd ? p[0] : p[1], s1 = odd ? p[2] : p[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (odd) { p[0] = s0; p[2] = s1; } else { p[1] = s0; p[3] = s1; }
+    s0 = hi ? p[0] : p[2];
+    s1 = hi ? p[1] : p[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (hi) { p[0] = s0; p[1] = s1; } else { p[2] = s0; p[3] = s1; }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+front_mma_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale, const float *__restrict__ in_shift,
+                 const float *__restrict__ A, const float *__restrict__ Bm, int C, size_t nframes,
+                 __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ R0) {
+    static_assert(CIN == 3, "A-row layout assumes 3 input channels");
+    extern __shared__ __align__(16) float sm[];
+    float *sA = sm;                                    // [3][17][17] adjacency
+    float *sx = sA + 3 * V17 * V17 + 1;                // [rows][CIN] normalised input
+    uint32_t *sam = reinterpret_cast<uint32_t *>(sx + kFrontFrames * V17 * CIN);   // [rows][kFrontLd] tf32 A rows
+    constexpr int kRows = kFrontFrames * V17;          // 272 = 17 m-tiles
+    for (int k = threadIdx.x; k < 3 * V17 * V17; k += blockDim.x) sA[k] = A[k];
+    const size_t f0 = (size_t)blockIdx.x * kFrontFrames;
+    const int nf = (int)(nframes - f0 < (size_t)kFrontFrames ? nframes - f0 : (size_t)kFrontFrames);
+    for (int e = threadIdx.x; e < nf * V17 * CIN; e += blockDim.x) {
+        const int vc = e % (V17 * CIN);
+        sx[e] = skel[f0 * V17 * CIN + e] * in_scale[vc] + in_shift[vc];
+    }
+    // this warp's B fragments: column group of 32 = 4 n-tiles, 2 k-steps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gr = lane >> 2, tg = lane & 3;
+    const int ngroups = 2 * C / 32;                    // 4 (C = 64) or 8 (C = 128)
+    const int grp = warp % ngroups, mt0 = warp / ngroups, mstep = 8 / ngroups;
+    uint32_t bf[2][4][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int col = grp * 32 + t * 8 + gr;
+            bf[ks][t][0] = __float_as_uint(__ldg(Bm + (size_t)(ks * 8 + tg) * 2 * C + col));
+            bf[ks][t][1] = __float_as_uint(__ldg(Bm + (size_t)(ks * 8 + tg + 4) * 2 * C + col));
+        }
+    __syncthreads();
+    // A rows: adjacency contraction of the row's frame, then the raw inputs, the bias one, zero padding
+    for (int u = threadIdx.x; u < kRows; u += blockDim.x) {
+        uint32_t *arow = sam + u * kFrontLd;
+        if (u < nf * V17) {
+            const int f = u / V17, w = u - f * V17;
+            float acc[3 * CIN];
+#pragma unroll
+            for (int k = 0; k < 3 * CIN; ++k) acc[k] = 0.f;
+            const float *xf = sx + f * V17 * CIN;
+#pragma unroll
+            for (int v = 0; v < V17; ++v) {
+                float x[CIN];
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) x[c] = xf[v * CIN + c];
+#pragma unroll
+                for (int pp = 0; pp < 3; ++pp) {
+                    const float a = sA[(pp * V17 + w) * V17 + v];
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) acc[pp * CIN + c] += a * x[c];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3 * CIN; ++k) arow[k] = to_tf32(acc[k]);
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) arow[3 * CIN + c] = to_tf32(sx[u * CIN + c]);
+            arow[12] = __float_as_uint(1.0f);
+            arow[13] = arow[14] = arow[15] = 0u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) arow[k] = 0u;
+        }
+    }
+    __syncthreads();
+    const bool is_y = grp * 32 < C;
+    __nv_bfloat16 *dst = is_y ? Y : R0;
+    const int cbase = is_y ? grp * 32 : grp * 32 - C;
+    for (int mt = mt0; mt < kRows / 16; mt += mstep) {
+        const int r0 = mt * 16 + gr, r1 = r0 + 8;
+        float acc[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a0 = sam[r0 * kFrontLd + ks * 8 + tg], a1 = sam[r1 * kFrontLd + ks * 8 + tg];
+            const uint32_t a2 = sam[r0 * kFrontLd + ks * 8 + tg + 4], a3 = sam[r1 * kFrontLd + ks * 8 + tg + 4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) mma_tf32(acc[t], a0, a1, a2, a3, bf[ks][t][0], bf[ks][t][1]);
+        }
+        const size_t g0 = (f0 * V17 + r0) * C, g1 = (f0 * V17 + r1) * C;
+        const bool v0 = r0 < nf * V17, v1 = r1 < nf * V17;
+        // pack, then transpose 4x4 inside the quad so that lane tg ends with the 8 columns of n-tile tg:
+        // one 16-byte store per lane and row (a quad writes 64 contiguous bytes) instead of four 4-byte ones
+        uint32_t p0[4], p1[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float y0 = acc[t][0], y1 = acc[t][1], y2 = acc[t][2], y3 = acc[t][3];
+            if (is_y) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+            p0[t] = gcn::pack_bf16(y0, y1);
+            p1[t] = gcn::pack_bf16(y2, y3);
+        }
+        quad_transpose(p0, tg);
+        quad_transpose(p1, tg);
+        const int col = cbase + tg * 8;
+        if (v0) *reinterpret_cast<uint4 *>(dst + g0 + col) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+        if (v1) *reinterpret_cast<uint4 *>(dst + g1 + col) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    }
+}
+
+// Host: the [16][2C] matrix of front_mma_kernel, rounded to TF32.
+inline void pack_front_matrix(const float *Wg, const float *bg, const float *Wr, const float *br, int C,
+                              std::vector<float> &out) {
+    out.assign((size_t)16 * 2 * C, 0.f);
+    for (int k = 0; k < 9; ++k)
+        for (int n = 0; n < C; ++n) out[(size_t)k * 2 * C + n] = Wg[(size_t)k * C + n];
+    for (int k = 0; k < 3; ++k)
+        for (int n = 0; n < C; ++n) out[(size_t)(9 + k) * 2 * C + C + n] = Wr[(size_t)k * C + n];
+    for (int n = 0; n < C; ++n) {
+        out[(size_t)12 * 2 * C + n] = bg[n];
+        out[(size_t)12 * 2 * C + C + n] = br[n];
+    }
+    for (float &x : out) {      // round to nearest TF32 (10 explicit mantissa bits)
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+        memcpy(&x, &u, 4);
     }
 }
 
@@ -361,6 +510,15 @@ int bf16_path_create(Ctx *ctx) {
         }
         GS_CUDA(cudaMalloc((void **)&bp->bias_t[i], C * sizeof(float)));
         GS_CUDA(cudaMemcpy(bp->bias_t[i], bias.data(), C * sizeof(float), cudaMemcpyHostToDevice));
+        // block 0 on tensor cores (front_mma_kernel): 3 input channels, a residual projection, C = 64 or 128;
+        // GOLFER_FRONT_FFMA=1 keeps the CUDA-core kernel
+        if (i == 0 && cin == 3 && b.has_res && (C == 64 || C == 128) && !getenv("GOLFER_FRONT_FFMA")) {
+            std::vector<float> bm;
+            pack_front_matrix(host(b.Wg), host(b.bg), host(b.Wr), host(b.br), C, bm);
+            GS_CUDA(cudaMalloc((void **)&bp->frontB, bm.size() * sizeof(float)));
+            ctx->ws_bytes += bm.size() * sizeof(float);
+            GS_CUDA(cudaMemcpy(bp->frontB, bm.data(), bm.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
     }
     return GS_OK;
 }
@@ -376,6 +534,7 @@ void bf16_path_destroy(Ctx *ctx) {
     for (auto &v : bp->stjP)
         for (float *p : v)
             if (p) cudaFree(p);
+    if (bp->frontB) cudaFree(bp->frontB);
     if (bp->trace) cudaFree(bp->trace);
     if (bp->trace_tc) cudaFree(bp->trace_tc);
     delete bp;
@@ -418,7 +577,16 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         const BlockMaps &m = bp->maps[i];
         const int C = b.c, cin = b.cin, cr = b.cr;
         bf *U = (bf *)ctx->bufU[i & 1];
-        if (i == 0) {
+        if (i == 0 && bp->frontB) {
+            const size_t smem = ((size_t)3 * V17 * V17 + 1 + (size_t)kFrontFrames * V17 * (cin + kFrontLd)) * sizeof(float);
+            {
+                LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
+                               rows * (cin * 4 + 4.0 * C));
+                front_mma_kernel<3><<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
+                    skel, ctx->in_scale, ctx->in_shift, b.A, bp->frontB, C, nframes, Y, R0);
+            }
+            GS_KERNEL_CHECK();
+        } else if (i == 0) {
             const size_t smem = (size_t)front_smem(cin, C).total * sizeof(float);
             if (smem > 48 * 1024)
                 GS_CUDA(cudaFuncSetAttribute(front_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
