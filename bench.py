@@ -538,7 +538,10 @@ def main():
                     "policy": f"fastest of {E2E_REPEATS} repetitions of {K} steps",
                     "all_repetitions": [world * N * K / t for t in al_runs]},
             "roofline": {"kernel": "dtw_wavefront", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
-                         "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None, "traffic": None,
+                         "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None,
+                         "traffic": (json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+                                     .get("dtw_wavefront", {}).get("bytes_per_launch")
+                                     if os.path.exists(os.path.join(ROOT, "profiles", "r1_traffic.json")) else None),
                          "note": "compulsory bytes 86,396 B/pair: HBM is not the binding limit (SURVEY.md 7 item 4); "
                                  "see fp32_pipe"},
         }
