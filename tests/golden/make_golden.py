@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 import golfer_b200  # noqa: E402
-from oracle import align, segnet  # noqa: E402
+from oracle import align, pose, segnet  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 TINY = golfer_b200.GolfSegConfig(version="tiny", widths=(16, 16, 32))
@@ -55,8 +55,36 @@ def golden_segnet():
     np.savez_compressed(os.path.join(HERE, "segnet_small.npz"), **out)
 
 
+def golden_next_rows():
+    """pose adapter and phase-conditioned alignment."""
+    out = {}
+    kp = pose.synth_keypoints(3, 20, seed=21, drop=0.15)
+    kp[1, :4, 11, 2] = 0.0          # leading frames without valid hips
+    kp[2, :, 5, 2] = 0.0            # never a valid torso: scale 1
+    out["pose_kp"] = kp
+    out["pose_out"] = pose.normalize_pose(kp, 0.3)
+    N, Ta, Tb = 3, 14, 11
+    a, b = align.synth_swings(N, Ta, Tb, seed=31)
+    rng = np.random.default_rng(5)
+    la = np.sort(rng.integers(0, 4, (N, Ta)), axis=1).astype(np.uint8)
+    lb = np.sort(rng.integers(0, 4, (N, Tb)), axis=1).astype(np.uint8)
+    maxL = Ta + Tb - 1
+    for tag, pen in (("soft", 0.5), ("hard", np.inf)):
+        cost = np.zeros(N, np.float32)
+        path = np.full((N, maxL, 2), -1, np.int32)
+        plen = np.zeros(N, np.int32)
+        for n in range(N):
+            c, p = align.align_phase_ref(a[n], b[n], la[n], lb[n], pen)
+            cost[n], plen[n] = c, len(p)
+            path[n, :len(p)] = p
+        out.update({f"phase_{tag}_cost": cost, f"phase_{tag}_path": path, f"phase_{tag}_plen": plen})
+    out.update({"phase_a": a, "phase_b": b, "phase_la": la, "phase_lb": lb})
+    np.savez_compressed(os.path.join(HERE, "next_rows_small.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_align()
     golden_segnet()
+    golden_next_rows()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -41,3 +41,17 @@ def test_feeds_the_segmenter_and_rejects_bad_shapes():
     with pytest.raises(golfer_b200.GolferError):
         golfer_b200.normalize_pose(torch.zeros(2, 4, 8, 3).cuda())
     assert golfer_b200.normalize_pose(torch.zeros(0, 4, 17, 3).cuda()).shape == (0, 4, 17, 3)
+
+
+def test_golden_fixtures_pose_and_phase(golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "next_rows_small.npz"))
+    got = golfer_b200.normalize_pose(torch.from_numpy(g["pose_kp"]).cuda(), 0.3).cpu().numpy()
+    assert np.array_equal(got, g["pose_out"])
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    for tag, pen in (("soft", 0.5), ("hard", float("inf"))):
+        cost, path, plen = golfer_b200.align_phase(dev(g["phase_a"]), dev(g["phase_b"]), dev(g["phase_la"]),
+                                                   dev(g["phase_lb"]), pen)
+        assert np.array_equal(cost.cpu().numpy(), g[f"phase_{tag}_cost"])
+        assert np.array_equal(path.cpu().numpy(), g[f"phase_{tag}_path"])
+        assert np.array_equal(plen.cpu().numpy(), g[f"phase_{tag}_plen"])

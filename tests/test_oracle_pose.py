@@ -99,3 +99,18 @@ def test_parsers_accept_the_pose_estimator_layouts(tmp_path):
     assert np.array_equal(golfer_b200.pose.load_keypoints_json(str(p), track_id=1), got)
     p.write_text(json.dumps(flat))
     assert np.array_equal(golfer_b200.pose.load_keypoints_json(str(p)), kp)
+
+
+def test_golden_pose_and_phase_fixtures(golden_dir):
+    import os
+    from oracle import align as oalign, align_native
+    g = np.load(os.path.join(golden_dir, "next_rows_small.npz"))
+    assert np.array_equal(opose.normalize_pose(g["pose_kp"], 0.3), g["pose_out"])
+    a, b, la, lb = g["phase_a"], g["phase_b"], g["phase_la"], g["phase_lb"]
+    for tag, pen in (("soft", 0.5), ("hard", np.inf)):
+        cost, path, plen = align_native.align_phase_batch_c(a, b, la, lb, pen)
+        assert np.array_equal(cost, g[f"phase_{tag}_cost"])
+        assert np.array_equal(path, g[f"phase_{tag}_path"]) and np.array_equal(plen, g[f"phase_{tag}_plen"])
+        for n in range(len(a)):
+            c, p = oalign.align_phase_ref(a[n], b[n], la[n], lb[n], pen)
+            assert c == g[f"phase_{tag}_cost"][n] and np.array_equal(p, g[f"phase_{tag}_path"][n, :len(p)])
