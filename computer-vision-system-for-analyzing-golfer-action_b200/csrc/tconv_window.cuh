@@ -324,15 +324,19 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                 mbar_wait(&tfull[buf], (n >> 1) & 1u);
                 if (leader) TW_TRACE(3 + g, (int)n, 6);
                 tc_fence_after();
+                // a warp whose 32 frames all lie past the end of the clip (last frame tile: T = 300 leaves 44 of
+                // 128 rows) skips the accumulator read and the row math; it still takes part in every handshake
+                const bool rows_live = ew * 32 < nvalid;
                 uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 64u + (uint32_t)(half * 32), acc);
+                if (rows_live) tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 64u + (uint32_t)(half * 32), acc);
                 if (!prm.proj) mbar_wait(&res_full[g * 3 + (int)es], eph);   // slot is ours and holds the residual box
-                tmem_ld_wait();
+                if (rows_live) tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tempty[buf]);
                 if (leader) TW_TRACE(3 + g, (int)n, 0);
                 unsigned char *rowp = box + (size_t)r * 128;
                 const float *bq = sbias + half * 32;
+                if (rows_live)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const float4 b0 = *reinterpret_cast<const float4 *>(bq + cc * 8);
