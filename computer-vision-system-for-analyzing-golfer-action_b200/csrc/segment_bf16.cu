@@ -31,7 +31,7 @@ struct BlockMaps {
 struct Bf16Path {
     std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
     std::vector<float *> bias_t;                        // b2 (+ br)
-    std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in TF32 fragment order (stj_tc_kernel)
+    std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in fp16 fragment order (stj_tc_kernel)
     float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
     std::vector<BlockMaps> maps;
     int maps_T = -1;
@@ -497,12 +497,6 @@ int bf16_path_create(Ctx *ctx) {
                 std::vector<float> packed;
                 if (w == 0) pack_stj_fragments(srcs[w], C, b.cj, Q == 1 ? 2 : 4, packed);
                 else pack_stj_fragments(srcs[w], b.cj, C, 4, packed);
-                for (float &x : packed) {      // round to nearest TF32 (10 explicit mantissa bits)
-                    uint32_t u;
-                    memcpy(&u, &x, 4);
-                    u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
-                    memcpy(&x, &u, 4);
-                }
                 GS_CUDA(cudaMalloc((void **)&bp->stjP[w][i], packed.size() * sizeof(float)));
                 ctx->ws_bytes += packed.size() * sizeof(float);
                 GS_CUDA(cudaMemcpy(bp->stjP[w][i], packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));

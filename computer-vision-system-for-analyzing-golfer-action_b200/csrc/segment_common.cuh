@@ -11,6 +11,8 @@
 //   gV[b,v,c] = a_v[b,v,c]
 // are applied by whichever kernel reads U next (next block's aggregation, head).
 #pragma once
+#include <cuda_fp16.h>
+#include <string.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -273,14 +275,16 @@ stj_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const flo
 }
 
 // ---- ST-joint attention on warp-level tensor cores (bf16 path) ----------------------------------
-// Same math as stj_kernel with both small GEMMs as mma.sync m16n8k8 TF32 (fp32 accumulate).  The
+// Same math as stj_kernel with both small GEMMs as mma.sync m16n8k16 FP16 (fp32 accumulate; fp16 has
+// TF32's 10-bit mantissa, twice the K per instruction and half the shared-memory bytes; operands are
+// clamped to the fp16 range when they are staged).  The
 // launch is PERSISTENT: one CTA per SM keeps the first-layer matrix W and ONE second-layer matrix
 // (Wt for the frame CTAs, Wv for the joint CTAs) resident in shared memory in B-fragment order and
 // walks 64-position items, so the weights are read from L2 once per CTA instead of once per k-step
 // and warp (the per-item form was bound by those loads: 168 us per C=256 launch for 5 GFLOP and
 // 160 MB).  While an item is in the MMAs the next item's pooled rows are already in flight to
 // registers.  Items: frame item = 64 frames of one clip; joint item = the 17 joints of 3 clips.
-// 16 warps = 4 (16-row slabs) x 4 (column groups).  Weights are rounded to TF32 once at context
+// 16 warps = 4 (16-row slabs) x 4 (column groups).  Weights are rounded to fp16 once at context
 // creation, activations when they are staged.  The fp32 parity path keeps stj_kernel (exact fp32).
 constexpr int kStjTcPos = 64;
 constexpr int kStjThreads = 512;
@@ -298,6 +302,18 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// A / B registers hold two fp16 each (consecutive k); D as for the TF32 form
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {     // (a -> low half), clamped to +-65504
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 // 1 / (1 + 2^(-x log2 e)) on the SFU approximations (rel. error ~1e-6, the bf16 path's bar is 1e-2)
 __device__ __forceinline__ float sigmoidf_fast(float x) {
     float e, r;
@@ -313,10 +329,10 @@ struct StjCfg {
     static constexpr int WN1 = (CJ / 8 < 4) ? CJ / 8 : 4;   // column groups that work in the first GEMM
     static constexpr int NT1 = CJ / 8 / WN1;                // n-tiles per warp, first GEMM
     static constexpr int NT2 = 2 * Q;                       // n-tiles per warp, second GEMM (C/4 columns)
-    static constexpr int LDP = C + 4, LDA = CJ + 4;         // +4 floats: conflict-free A-fragment loads
+    static constexpr int LDP = C / 2 + 4, LDA = CJ / 2 + 4; // row strides in 32-bit words (2 fp16 each); +4: conflict-free A-fragment loads
     static constexpr int NPF = kStjTcPos * C / 4 / kStjThreads;   // float4 per thread and item
     static constexpr size_t smem_bytes =
-        ((size_t)2 * C * CJ + (size_t)kStjTcPos * (LDP + LDA) + CJ + 2 * C) * sizeof(float);
+        ((size_t)C * CJ + (size_t)kStjTcPos * (LDP + LDA) + CJ + 2 * C) * sizeof(float);
 };
 
 template <int V, int Q>
@@ -329,10 +345,10 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
     constexpr int C = Cf::C, cj = Cf::CJ, NT1 = Cf::NT1, NT2 = Cf::NT2, WN1 = Cf::WN1, ldp = Cf::LDP, lda = Cf::LDA;
     constexpr int NPF = Cf::NPF, C4 = C / 4, KC = kStjClipsPerJointItem;
     extern __shared__ __align__(16) float sm[];
-    float *w1 = sm;                                               // [C/8][WN1][NT1*2 floats][32 lanes] fragments
-    float *w2 = w1 + C * cj;                                      // [cj/8][4][NT2/2 float4][32 lanes]
-    uint32_t *sp = reinterpret_cast<uint32_t *>(w2 + cj * C);     // pooled [64][ldp] tf32
-    uint32_t *sa = sp + kStjTcPos * ldp;                          // hidden [64][lda] tf32
+    float *w1 = sm;                                               // [C/16][WN1][NT1*2 words][32 lanes] fragments (2 fp16 per word)
+    float *w2 = w1 + C * cj / 2;                                  // [cj/16][4][NT2/2 x 4 words][32 lanes]
+    uint32_t *sp = reinterpret_cast<uint32_t *>(w2 + cj * C / 2); // pooled [64][ldp] fp16 pairs
+    uint32_t *sa = sp + kStjTcPos * ldp;                          // hidden [64][lda] fp16 pairs
     float *s_b1 = reinterpret_cast<float *>(sa + kStjTcPos * lda);   // [cj] first-layer bias
     float *s_b2 = s_b1 + cj;                                      // [C]  second-layer bias
     float *s_se = s_b2 + C;                                       // [C]  SE gate of the item's clip (frame items)
@@ -344,7 +360,7 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
     {
         const float4 *g1 = reinterpret_cast<const float4 *>(P1);
         const float4 *g2 = reinterpret_cast<const float4 *>(is_t ? P2t : P2v);
-        for (int e = threadIdx.x; e < C * cj / 4; e += kStjThreads) {
+        for (int e = threadIdx.x; e < C * cj / 8; e += kStjThreads) {
             reinterpret_cast<float4 *>(w1)[e] = __ldg(g1 + e);
             reinterpret_cast<float4 *>(w2)[e] = __ldg(g2 + e);
         }
@@ -396,7 +412,7 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
     for (int item = first; item < nitems; item += stride) {
         int clip0, p0;
         decode(item, clip0, p0);
-        // stage the prefetched rows: oracle order (sum / count) scaled by the SE gate, rounded to TF32
+        // stage the prefetched rows: oracle order (sum / count) scaled by the SE gate, rounded to fp16
 #pragma unroll
         for (int k = 0; k < NPF; ++k) {
             const int row = srow0 + k * srow_step;
@@ -406,9 +422,9 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
                 s4 = q == 0 ? pse[0] : (q == 1 ? pse[1] : pse[2]);
             }
             const float4 v4 = pre[k];
-            *reinterpret_cast<uint4 *>(sp + row * ldp + sc) =
-                make_uint4(to_tf32(s4.x * (v4.x * inv)), to_tf32(s4.y * (v4.y * inv)), to_tf32(s4.z * (v4.z * inv)),
-                           to_tf32(s4.w * (v4.w * inv)));
+            *reinterpret_cast<uint2 *>(sp + row * ldp + sc / 2) =
+                make_uint2(pack_half2_sat(s4.x * (v4.x * inv), s4.y * (v4.y * inv)),
+                           pack_half2_sat(s4.z * (v4.z * inv), s4.w * (v4.w * inv)));
         }
         if (srow0 == 0) *reinterpret_cast<float4 *>(s_se + sc) = pse[0];
         __syncthreads();
@@ -420,8 +436,8 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
 #pragma unroll 4
-            for (int ks = 0; ks < C / 8; ++ks) {
-                const int k0 = ks * 8;
+            for (int ks = 0; ks < C / 16; ++ks) {
+                const int k0 = ks * 8;                 // in 32-bit words: 16 fp16 per k-step
                 const uint32_t a0 = sp[r0 * ldp + k0 + tg], a1 = sp[r1 * ldp + k0 + tg];
                 const uint32_t a2 = sp[r0 * ldp + k0 + tg + 4], a3 = sp[r1 * ldp + k0 + tg + 4];
                 float bf[NT1 * 2];
@@ -435,16 +451,14 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
                 }
 #pragma unroll
                 for (int t = 0; t < NT1; ++t)
-                    mma_tf32(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
+                    mma_f16(acc[t], a0, a1, a2, a3, __float_as_uint(bf[2 * t]), __float_as_uint(bf[2 * t + 1]));
             }
 #pragma unroll
             for (int t = 0; t < NT1; ++t) {
                 const int col = wn * (NT1 * 8) + t * 8 + 2 * tg;
                 const float b0 = s_b1[col], b1 = s_b1[col + 1];
-                *reinterpret_cast<uint2 *>(sa + r0 * lda + col) =
-                    make_uint2(to_tf32(hardswishf(acc[t][0] + b0)), to_tf32(hardswishf(acc[t][1] + b1)));
-                *reinterpret_cast<uint2 *>(sa + r1 * lda + col) =
-                    make_uint2(to_tf32(hardswishf(acc[t][2] + b0)), to_tf32(hardswishf(acc[t][3] + b1)));
+                sa[r0 * lda + col / 2] = pack_half2_sat(hardswishf(acc[t][0] + b0), hardswishf(acc[t][1] + b1));
+                sa[r1 * lda + col / 2] = pack_half2_sat(hardswishf(acc[t][2] + b0), hardswishf(acc[t][3] + b1));
             }
         }
         __syncthreads();
@@ -455,7 +469,7 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < cj / 8; ++ks) {
+            for (int ks = 0; ks < cj / 16; ++ks) {
                 const int k0 = ks * 8;
                 const uint32_t a0 = sa[r0 * lda + k0 + tg], a1 = sa[r1 * lda + k0 + tg];
                 const uint32_t a2 = sa[r0 * lda + k0 + tg + 4], a3 = sa[r1 * lda + k0 + tg + 4];
@@ -463,8 +477,8 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
 #pragma unroll
                 for (int i = 0; i < NT2 / 2; ++i) {
                     const float4 v = pk[i * 32];
-                    mma_tf32(acc[2 * i], a0, a1, a2, a3, __float_as_uint(v.x), __float_as_uint(v.y));
-                    mma_tf32(acc[2 * i + 1], a0, a1, a2, a3, __float_as_uint(v.z), __float_as_uint(v.w));
+                    mma_f16(acc[2 * i], a0, a1, a2, a3, __float_as_uint(v.x), __float_as_uint(v.y));
+                    mma_f16(acc[2 * i + 1], a0, a1, a2, a3, __float_as_uint(v.z), __float_as_uint(v.w));
                 }
             }
             const long long ri0 = row_index(clip0, p0, r0), ri1 = row_index(clip0, p0, r1);
@@ -487,24 +501,30 @@ stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const 
     }
 }
 
-// Host: re-pack W [K][N] (row-major) into mma.sync m16n8k8 B-fragment order for `wn` column groups of
-// N/wn columns (nt = N/wn/8 n-tiles each).  A lane's registers for one k-step are
-//   frag[t*2 + h] = W[ks*8 + (lane&3) + 4h][g*(N/wn) + t*8 + (lane>>2)],  t < nt, h < 2,
-// stored in chunks of `cw` floats (cw = 2 when nt == 1, else 4) with the 32 lanes of a chunk contiguous:
+// Host: re-pack W [K][N] (row-major) into mma.sync m16n8k16 fp16 B-fragment order for `wn` column groups of
+// N/wn columns (nt = N/wn/8 n-tiles each).  A lane's registers for one 16-deep k-step are
+//   frag[t*2 + h] = {W[k][col], W[k+1][col]} as two fp16 (k in the low half),
+//   k = ks*16 + 2*(lane&3) + 8h,  col = g*(N/wn) + t*8 + (lane>>2),  t < nt, h < 2,
+// stored in chunks of `cw` words (cw = 2 when nt == 1, else 4) with the 32 lanes of a chunk contiguous:
 //   out[(((ks*wn + g) * (2*nt/cw) + chunk) * 32 + lane) * cw + e] = frag[chunk*cw + e]
-// so every warp-wide fragment load is one conflict-free 8- or 16-byte access per lane.
+// so every warp-wide fragment load is one conflict-free 8- or 16-byte access per lane.  `out` carries
+// the 32-bit words in float storage (K*N/2 of them).
 inline void pack_stj_fragments(const float *W, int K, int N, int wn, std::vector<float> &out) {
     const int nt = N / wn / 8, cw = nt == 1 ? 2 : 4, nchunk = 2 * nt / cw;
-    out.assign((size_t)K * N, 0.f);
-    for (int ks = 0; ks < K / 8; ++ks)
+    out.assign((size_t)K * N / 2, 0.f);
+    for (int ks = 0; ks < K / 16; ++ks)
         for (int g = 0; g < wn; ++g)
             for (int lane = 0; lane < 32; ++lane)
                 for (int t = 0; t < nt; ++t)
                     for (int h = 0; h < 2; ++h) {
                         const int f = t * 2 + h, chunk = f / cw, e = f % cw;
-                        const int k = ks * 8 + (lane & 3) + 4 * h;
+                        const int k = ks * 16 + 2 * (lane & 3) + 8 * h;
                         const int col = g * (N / wn) + t * 8 + (lane >> 2);
-                        out[((((size_t)ks * wn + g) * nchunk + chunk) * 32 + lane) * cw + e] = W[(size_t)k * N + col];
+                        const __half lo = __float2half_rn(W[(size_t)k * N + col]);
+                        const __half hi = __float2half_rn(W[(size_t)(k + 1) * N + col]);
+                        const uint32_t word = (uint32_t)(*reinterpret_cast<const unsigned short *>(&lo)) |
+                                              ((uint32_t)(*reinterpret_cast<const unsigned short *>(&hi)) << 16);
+                        memcpy(&out[((((size_t)ks * wn + g) * nchunk + chunk) * 32 + lane) * cw + e], &word, 4);
                     }
 }
 
