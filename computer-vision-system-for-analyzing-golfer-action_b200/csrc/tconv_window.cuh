@@ -364,10 +364,10 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                         f[2 * e] = fmaxf(f[2 * e], 0.f);
                         f[2 * e + 1] = fmaxf(f[2 * e + 1], 0.f);
                         pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                        // frame pooling (sum over joints) of the stored (bf16-rounded) values
-                        const float2 rt = __bfloat1622float2(pp[e]);
-                        pt[cc * 8 + 2 * e] += rt.x;
-                        pt[cc * 8 + 2 * e + 1] += rt.y;
+                        // frame pooling (sum over joints) of the fp32 values, as the oracle pools (the stored
+                        // copy is their bf16 rounding; re-expanding it cost 2 more instructions per pair)
+                        pt[cc * 8 + 2 * e] += f[2 * e];
+                        pt[cc * 8 + 2 * e + 1] += f[2 * e + 1];
                     }
                     *sp = packed;
                 }
