@@ -17,7 +17,7 @@ namespace {
 
 constexpr int kLShoulder = 5, kRShoulder = 6, kLHip = 11, kRHip = 12;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 normalize_pose_kernel(const float *__restrict__ kp, float *__restrict__ out, int T, int V, float thr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *cx = reinterpret_cast<float *>(smem_raw);     // hip centre, then filled centre
@@ -90,7 +90,7 @@ int normalize_pose_launch(Ctx *ctx, const float *kp, float *out, int B, int T, i
         GS_CUDA(cudaFuncSetAttribute(normalize_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(ctx, K_POSE, st, 8.0 * B * T * V, 24.0 * B * T * V);
-        normalize_pose_kernel<<<B, 256, smem, st>>>(kp, out, T, V, min_score);
+        normalize_pose_kernel<<<B, T * V >= 4096 ? 1024 : 256, smem, st>>>(kp, out, T, V, min_score);
     }
     GS_KERNEL_CHECK();
     return GS_OK;

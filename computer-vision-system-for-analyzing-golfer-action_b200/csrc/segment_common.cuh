@@ -163,9 +163,19 @@ se_kernel(const float *__restrict__ PVpart, int T, int C, int cs, int nchunk, in
         hid[threadIdx.x] = fmaxf(acc, 0.f);
     }
     __syncthreads();
+    // FC2: K = cs split over the G groups in contiguous ranges (a 64-deep chain of dependent L2 loads in one
+    // group was most of this kernel's latency), partials folded in group order: still a fixed summation order
+    if (g < G) {
+        const int per = (cs + G - 1) / G, k0 = g * per, k1 = min(cs, k0 + per);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) acc += hid[k] * __ldg(W2 + k * C + c);
+        part[g * C + c] = acc;
+    }
+    __syncthreads();
     if (g == 0) {
         float acc = b2[c];
-        for (int k = 0; k < cs; ++k) acc += hid[k] * W2[k * C + c];
+        for (int k = 0; k < G; ++k) acc += part[k * C + c];
         seS[(size_t)b * C + c] = sigmoidf_acc(acc);
     }
 }
