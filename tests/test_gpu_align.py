@@ -201,3 +201,18 @@ def test_phase_alignment_rejects_bad_arguments():
         golfer_b200.align_phase(a, b, la, la, 1.0)                      # host arrays
     with pytest.raises(golfer_b200.GolferError):
         golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(la), float("nan"))
+
+
+def test_four_byte_aligned_inputs():
+    # a view whose data pointer is only 4-byte aligned: the staging copies must fall back from 8-byte cp.async
+    N, Ta, Tb = 5, 90, 70
+    a, b = oalign.synth_swings(N, Ta, Tb, seed=77)
+    fa = torch.zeros(a.size + 1, device="cuda")
+    fb = torch.zeros(b.size + 1, device="cuda")
+    fa[1:] = torch.from_numpy(a).cuda().flatten()
+    fb[1:] = torch.from_numpy(b).cuda().flatten()
+    va, vb = fa[1:].view(N, Ta, 17, 2), fb[1:].view(N, Tb, 17, 2)
+    assert va.data_ptr() % 8 == 4 and va.is_contiguous()
+    ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 4)
+    cost, path, plen = golfer_b200.host.align_batch(va, vb)
+    _check_against(a, b, cost, path, plen, ref_cost, ref_path, ref_plen)
