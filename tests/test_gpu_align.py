@@ -33,7 +33,11 @@ def test_golden_fixtures(golden_dir):
 
 
 @pytest.mark.parametrize("N,Ta,Tb,Cc", [(5, 300, 300, 2), (4, 300, 257, 3), (3, 64, 300, 2), (2, 1, 1, 2),
-                                        (3, 1, 33, 2), (3, 33, 1, 2), (6, 17, 31, 2), (2, 500, 420, 2)])
+                                        (3, 1, 33, 2), (3, 33, 1, 2), (6, 17, 31, 2), (2, 500, 420, 2),
+                                        # many more pairs than resident CTAs (each CTA pipelines several pairs),
+                                        # tiny shapes, odd / even column counts around the two-column mapping
+                                        (9000, 24, 24, 2), (7001, 9, 5, 2), (4, 2, 2, 2), (5, 3, 2, 2), (3, 65, 64, 2),
+                                        (3, 66, 65, 3), (2, 1024, 1000, 2)])
 def test_matches_oracle_bitwise(N, Ta, Tb, Cc):
     a, b = oalign.synth_swings(N, Ta, Tb, C=Cc, seed=Ta * 7 + Tb)
     ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 4)
@@ -161,7 +165,7 @@ def _phase_labels(N, T, seed, nphase=5):
 
 @pytest.mark.parametrize("N,Ta,Tb,pen", [(6, 300, 300, 0.5), (5, 300, 257, 2.0), (4, 64, 300, 0.5), (3, 1, 1, 1.0),
                                          (4, 33, 1, 1.0), (5, 300, 300, float("inf")), (4, 120, 90, 0.0),
-                                         (700, 40, 40, 0.75)])
+                                         (700, 40, 40, 0.75), (9000, 20, 19, 0.3), (3, 2, 1, 1.5), (4, 65, 33, 0.25)])
 def test_phase_alignment_matches_oracle_bitwise(N, Ta, Tb, pen):
     a, b = oalign.synth_swings(N, Ta, Tb, seed=Ta * 5 + Tb)
     la, lb = _phase_labels(N, Ta, 1), _phase_labels(N, Tb, 2)
