@@ -650,6 +650,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.ttiles = cdiv(T, tw::kFramesTile);
             q.nboxes = C / 64;
             q.nq_items = B * q.ttiles;
+            static const bool tw_rev = getenv("GOLFER_TCONV_FWD") == nullptr;
+            q.rev = tw_rev ? 1 : 0;
             q.bias = bp->bias_t[i];
             q.PT = ctx->PT;
             q.PVpart = ctx->PVpart;

@@ -46,6 +46,7 @@ struct Params {
     int dil[GS_MAX_BRANCHES];
     int dmax, wrows;  // window rows = 128 + 2*dmax
     int ttiles, nboxes, nq_items;   // frame tiles per clip, 64-channel boxes, items per box (B * ttiles)
+    int rev;              // 1: walk the items from the last clip down (reads the tail of H, still in L2, first)
     int stages, eslots;   // A ring depth; staging slots per epilogue group (2 or 3)
     uint32_t a_span, xg_off, stage_bytes, w_off, wr_off, w_bytes, wr_bytes, out_off, scr_off, bar_off, total;
     const float *bias;    // [C]  (b2 + folded projection bias)
@@ -163,7 +164,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
                 for (int g = 0; g < 2; ++g) {
                     const int item = i0 + g * ctas_per_box;
                     if (item >= prm.nq_items) continue;
-                    const int b = item / prm.ttiles, t0 = (item % prm.ttiles) * kFramesTile;
+                    const int itm = prm.rev ? prm.nq_items - 1 - item : item;
+                    const int b = itm / prm.ttiles, t0 = (itm % prm.ttiles) * kFramesTile;
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = smem + (size_t)stage * prm.stage_bytes;
                     if (elect_one()) {
@@ -266,7 +268,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
             const int g = 3 - warp;
             uint32_t ecnt = 0;
             for (int i0 = first_item + g * ctas_per_box; i0 < prm.nq_items; i0 += item_stride) {
-                const int b = i0 / prm.ttiles, t0 = (i0 % prm.ttiles) * kFramesTile;
+                const int itm = prm.rev ? prm.nq_items - 1 - i0 : i0;
+                const int b = itm / prm.ttiles, t0 = (itm % prm.ttiles) * kFramesTile;
                 for (int v = 0; v < 17; ++v) {
                     const uint32_t sl = ecnt % (uint32_t)ES, ph = (ecnt / (uint32_t)ES) & 1u;
                     uint64_t *rf = &res_full[g * 3 + (int)sl];
@@ -311,7 +314,8 @@ tconv_window_kernel(const __grid_constant__ Maps maps, const __grid_constant__ P
             }
         };
         for (int i0 = first_item + g * ctas_per_box; i0 < prm.nq_items; i0 += item_stride) {
-            const int b = i0 / prm.ttiles, tt = i0 % prm.ttiles, t0 = tt * kFramesTile;
+            const int itm = prm.rev ? prm.nq_items - 1 - i0 : i0;
+            const int b = itm / prm.ttiles, tt = itm % prm.ttiles, t0 = tt * kFramesTile;
             const int nvalid = min(kFramesTile, T - t0);
             float pt[32];
 #pragma unroll
