@@ -377,6 +377,8 @@ int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, c
     base_program(L.prog, B, T, N, 64, 1, out_joint_major ? gcn::kRowsPerTile : tc::kTileM);
     L.prog.trace = trace;
     L.prog.out_joint_major = out_joint_major ? 1 : 0;
+    static const bool gemm_rev = getenv("GOLFER_GEMM_FWD") == nullptr;
+    L.prog.rev = gemm_rev ? 1 : 0;
     L.prog.nchunks = K / 64;
     L.prog.b_bytes[0] = N * 64 * 2;
     for (int k = 0; k < L.prog.nchunks; ++k) {
@@ -650,7 +652,10 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.ttiles = cdiv(T, tw::kFramesTile);
             q.nboxes = C / 64;
             q.nq_items = B * q.ttiles;
-            static const bool tw_rev = getenv("GOLFER_TCONV_FWD") == nullptr;
+            // traversal order: the branch 1x1 GEMM walks its tiles from the last clip down (it then finds the tail
+            // of the GCN's Y still in L2: 2-4 % on that launch), so the tail of ITS output H is the first clips and
+            // this kernel walks forward (GOLFER_GEMM_FWD=1 / GOLFER_TCONV_REV=1 flip either: measured within 1 %)
+            static const bool tw_rev = getenv("GOLFER_TCONV_REV") != nullptr;
             q.rev = tw_rev ? 1 : 0;
             q.bias = bp->bias_t[i];
             q.PT = ctx->PT;

@@ -58,6 +58,7 @@ struct Program {
     int N;              // accumulator columns used (multiple of 64, <= 256)
     int mtiles;         // row tiles per clip
     int ntiles;         // total tiles = B * mtiles
+    int rev;            // 1: walk the tiles from the last clip down (the producer's most recent output is in L2)
     int rows_per_clip;  // T * V
     int relu;
     int has_residual;   // add residual[b, r, n] (bf16, TMA-loaded through mapRes) before the activation
@@ -315,8 +316,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int stage = 0, tcount = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < prog.ntiles; tile += gridDim.x, ++tcount) {
-            const int b = tile / prog.mtiles;
-            const int row0 = (tile % prog.mtiles) * prog.tile_rows;
+            const int tl = prog.rev ? prog.ntiles - 1 - tile : tile;
+            const int b = tl / prog.mtiles;
+            const int row0 = (tl % prog.mtiles) * prog.tile_rows;
             for (int c = 0; c < prog.nchunks; ++c) {
                 const Chunk &ch = prog.ch[c];
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -388,8 +390,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t box_bytes = (uint32_t)prog.tile_rows * 128u;
             int it = g;
             for (int tile = blockIdx.x + g * gridDim.x; tile < prog.ntiles; tile += 2 * gridDim.x, it += 2) {
-                const int b = tile / prog.mtiles;
-                const int row0 = (tile % prog.mtiles) * prog.tile_rows;
+                const int tl = prog.rev ? prog.ntiles - 1 - tile : tile;
+                const int b = tl / prog.mtiles;
+                const int row0 = (tl % prog.mtiles) * prog.tile_rows;
                 for (int q = 0; q < N / 64; ++q) {
                     const uint32_t sl = ecnt % (uint32_t)ES, ph = (ecnt / (uint32_t)ES) & 1;
                     uint64_t *rf = &res_full[g * 2 + (int)sl];
@@ -421,8 +424,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int it = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < prog.ntiles; tile += 2 * gridDim.x, it += 2) {
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-            const int b = tile / prog.mtiles;
-            const int mt = tile % prog.mtiles;
+            const int tl = prog.rev ? prog.ntiles - 1 - tile : tile;
+            const int b = tl / prog.mtiles;
+            const int mt = tl % prog.mtiles;
             const int row0 = mt * prog.tile_rows;
             mbar_wait(&tfull[g], acc_phase);
             if (leader) TC_TRACE(3 + g, it >> 1, 0);
