@@ -62,6 +62,7 @@ struct Params {
     int Cin, C, T, B;
     int mtiles, ntiles, rows_per_clip;
     int xslots, wstages, eslots, nacc;
+    int rev;              // 1: walk the tiles from the last clip down (the tail of the previous block's U is in L2)
     const float *gT;      // [B,T,Cin]   (maps carry the data; non-null = gating on)
     const float *gV;      // [B,17,Cin]
     const float *A;       // [3,17,17] fp32
@@ -254,8 +255,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         int slot = 0, tcount = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int b = tile / prm.mtiles;
-            const int mt = tile % prm.mtiles;
+            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int b = tl / prm.mtiles;
+            const int mt = tl % prm.mtiles;
             const int row0 = mt * kRowsPerTile;
             for (int cb = 0; cb < nbc; ++cb) {
                 unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
@@ -401,8 +403,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int b = tile / prm.mtiles;
-            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int b = tl / prm.mtiles;
+            const int row0 = (tl % prm.mtiles) * kRowsPerTile;
             for (int cb = 0; cb < nbc; ++cb) {
                 unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
                 mbar_wait(&x_full[slot], ph);
@@ -474,8 +477,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         uint32_t acc_cnt = 0, ecnt = 0;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int b = tile / prm.mtiles;
-            const int row0 = (tile % prm.mtiles) * kRowsPerTile;
+            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int b = tl / prm.mtiles;
+            const int row0 = (tl % prm.mtiles) * kRowsPerTile;
             const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
             mbar_wait(&acc_full[as], aph);
             if (leader) GCN_TRACE(4, tcount, 0);

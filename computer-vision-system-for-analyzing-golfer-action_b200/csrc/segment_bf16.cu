@@ -611,6 +611,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.ntiles = B * q.mtiles;
             q.gT = ctx->gT;
             q.gV = ctx->gV;
+            static const bool gcn_rev = getenv("GOLFER_GCN_REV") != nullptr;
+            q.rev = gcn_rev ? 1 : 0;
             q.A = b.A;
             q.bias = b.bg;
             q.dbg_xa = (bp->debug_xa && cin * 128 <= 119 * 256) ? XA : nullptr;
