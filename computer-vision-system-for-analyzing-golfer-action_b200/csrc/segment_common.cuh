@@ -681,7 +681,8 @@ head_stream_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const
                    uint8_t *__restrict__ labels) {
     extern __shared__ __align__(16) float sm[];     // gV[b]: [V][C], then WhT: [K][C], both lane-interleaved
     float *sgv = sm, *swh = sm + V * C;
-    const int b = blockIdx.y;
+    // last clips first: the producing kernel wrote them last, so they are the ones still in L2
+    const int b = gridDim.y - 1 - blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = lane >> 3, g = lane & 7;
     const int t = blockIdx.x * kHeadFrames + warp * 4 + f;
