@@ -4,11 +4,44 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
 namespace gs {
 
 static thread_local char g_err[512] = "";
+
+namespace {
+std::mutex g_attr_mu;
+std::map<std::pair<int, const void *>, size_t> g_dyn_smem;                        // (device, kernel) -> opted-in bytes
+std::map<std::tuple<int, const void *, int, size_t>, int> g_occupancy;            // (device, kernel, threads, smem)
+}  // namespace
+
+int ensure_dyn_smem(Ctx *ctx, const void *kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return GS_OK;
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t &have = g_dyn_smem[{ctx->device, kernel}];
+    if (bytes <= have) return GS_OK;
+    GS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return GS_OK;
+}
+
+int cached_occupancy(Ctx *ctx, const void *kernel, int nthreads, size_t smem_bytes, int *blocks_per_sm) {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    const auto key = std::make_tuple(ctx->device, kernel, nthreads, smem_bytes);
+    auto it = g_occupancy.find(key);
+    if (it == g_occupancy.end()) {
+        int n = 0;
+        GS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nthreads, smem_bytes));
+        it = g_occupancy.emplace(key, n < 1 ? 1 : n).first;
+    }
+    *blocks_per_sm = it->second;
+    return GS_OK;
+}
 
 const char *kernel_name(int id) {
     static const char *names[K_COUNT] = {
@@ -190,6 +223,7 @@ void free_ctx(Ctx *ctx) {
     }
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
     delete ctx;
 }
 
@@ -209,6 +243,18 @@ int check_segment_args(Ctx *ctx, const void *in, int B, int T) {
         set_error("bad segment arguments: B=%d (max %d) T=%d (max %d)", B, ctx->max_B, T, ctx->max_T);
         return GS_ERR_INVALID;
     }
+    return GS_OK;
+}
+
+// workspace ordering between calls on different streams (Ctx::ev_last)
+int order_after_previous(Ctx *ctx, cudaStream_t st) {
+    if (ctx->ev_last_valid && ctx->last_stream != st) GS_CUDA(cudaStreamWaitEvent(st, ctx->ev_last, 0));
+    return GS_OK;
+}
+int mark_done(Ctx *ctx, cudaStream_t st) {
+    GS_CUDA(cudaEventRecord(ctx->ev_last, st));
+    ctx->ev_last_valid = true;
+    ctx->last_stream = st;
     return GS_OK;
 }
 
@@ -276,7 +322,8 @@ int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weight
             }
         }
         if (rc) break;
-        if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+        if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming) != cudaSuccess) {
             set_error("event creation failed");
             rc = GS_ERR_CUDA;
             break;
@@ -346,12 +393,13 @@ int gs_segment(gs_ctx *h, const float *skel_dev, float *logits_dev, uint8_t *lab
     }
     GS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if ((rc = order_after_previous(ctx, st))) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_start, st));
     rc = forward(ctx, skel_dev, logits_dev, labels_dev, B, T, -1, nullptr, st);
     if (rc) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
     ctx->ev_valid = true;
-    return GS_OK;
+    return mark_done(ctx, st);
 }
 
 int gs_segment_features(gs_ctx *h, const float *skel_dev, int block, float *out_dev, int B, int T,
@@ -364,7 +412,10 @@ int gs_segment_features(gs_ctx *h, const float *skel_dev, int block, float *out_
         return GS_ERR_INVALID;
     }
     GS_CUDA(cudaSetDevice(ctx->device));
-    return forward(ctx, skel_dev, nullptr, nullptr, B, T, block, out_dev, (cudaStream_t)cuda_stream);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if ((rc = order_after_previous(ctx, st))) return rc;
+    if ((rc = forward(ctx, skel_dev, nullptr, nullptr, B, T, block, out_dev, st))) return rc;
+    return mark_done(ctx, st);
 }
 
 int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8_t *labels_host, int B,
@@ -376,20 +427,17 @@ int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8
     const gs_config &c = ctx->cfg;
     const size_t in_per = (size_t)T * c.num_joints * c.in_channels;
     const size_t out_per = (size_t)T * c.num_classes;
-    // Clips are independent: split the batch in chunks; H2D of chunk i+1 (copy stream)
-    // overlaps the kernels of chunk i (compute stream); D2H follows each chunk.
-    // Chunk schedule: a small first chunk gets the kernels started early, the rest follows in equal parts
-    // (GOLFER_HOST_CHUNKS = number of chunks, GOLFER_HOST_FIRST = clips in the first chunk).
-    static const int env_chunks = getenv("GOLFER_HOST_CHUNKS") ? atoi(getenv("GOLFER_HOST_CHUNKS")) : 0;
-    static const int env_first = getenv("GOLFER_HOST_FIRST") ? atoi(getenv("GOLFER_HOST_FIRST")) : 0;
-    // measured at B = 256 (e2e clips/s): 1 chunk 42.8 k, 2 equal 42.1 k, 2 with a quarter first 43.2 k,
-    // 3 chunks 35-41 k, 4 equal 37.4 k: the persistent kernels lose efficiency on small batches faster than
-    // the 15.7 MB input copy (~0.35 ms) is worth hiding
-    const int nchunks = env_chunks > 0 ? (env_chunks < B ? env_chunks : B) : (B >= 16 ? 2 : 1);
-    int first = env_first > 0 && env_first < B && nchunks > 1 ? env_first
-                                                               : (env_chunks > 0 ? (B + nchunks - 1) / nchunks : (B >= 16 ? B / 4 : B));
+    // Clips are independent: split the batch in two chunks; the H2D of the second (copy stream) overlaps
+    // the kernels of the first (compute stream); D2H follows each chunk.  A quarter-size first chunk gets the
+    // kernels started early.  Measured at B = 256 (e2e clips/s): 1 chunk 42.8 k, 2 equal 42.1 k, 2 with a
+    // quarter first 43.2 k, 3 chunks 35-41 k, 4 equal 37.4 k: the persistent kernels lose efficiency on small
+    // batches faster than the 15.7 MB input copy (~0.35 ms) is worth hiding.
+    const int nchunks = B >= 16 ? 2 : 1;
+    const int first = B >= 16 ? B / 4 : B;
     const int rest = nchunks > 1 ? (B - first + nchunks - 2) / (nchunks - 1) : B;
     cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
+    if ((rc = order_after_previous(ctx, sc))) return rc;
+    if ((rc = order_after_previous(ctx, sx))) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_start, sc));
     for (int k = 0, b0 = 0; b0 < B; ++k) {
         const int per = k == 0 ? first : rest;
@@ -413,6 +461,7 @@ int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8
     }
     GS_CUDA(cudaEventRecord(ctx->ev_stop, sc));
     ctx->ev_valid = true;
+    if ((rc = mark_done(ctx, sc))) return rc;
     GS_CUDA(cudaStreamSynchronize(sc));
     return GS_OK;
 }
@@ -440,12 +489,13 @@ int gs_align(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, i
     }
     GS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if ((rc = order_after_previous(ctx, st))) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_start, st));
     rc = align_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_dev, path_dev, path_len_dev, st);
     if (rc) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
     ctx->ev_valid = true;
-    return GS_OK;
+    return mark_done(ctx, st);
 }
 
 int gs_align_phase(gs_ctx *h, const float *a_dev, const float *b_dev, const uint8_t *labels_a_dev,
@@ -464,13 +514,14 @@ int gs_align_phase(gs_ctx *h, const float *a_dev, const float *b_dev, const uint
     }
     GS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if ((rc = order_after_previous(ctx, st))) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_start, st));
     rc = align_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_dev, path_dev, path_len_dev, st, labels_a_dev,
                       labels_b_dev, penalty);
     if (rc) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
     ctx->ev_valid = true;
-    return GS_OK;
+    return mark_done(ctx, st);
 }
 
 int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, int Ta, int Tb, int V, int Cc,
@@ -496,6 +547,8 @@ int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, in
     const int nchunks = N >= 64 ? 4 : 1;
     const int per = (N + nchunks - 1) / nchunks;
     cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
+    if ((rc = order_after_previous(ctx, sc))) return rc;
+    if ((rc = order_after_previous(ctx, sx))) return rc;
     GS_CUDA(cudaEventRecord(ctx->ev_start, sc));
     for (int k = 0, n0 = 0; n0 < N; ++k, n0 += per) {
         const int cnt = (N - n0) < per ? (N - n0) : per;
@@ -521,6 +574,7 @@ int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, in
     }
     GS_CUDA(cudaEventRecord(ctx->ev_stop, sc));
     ctx->ev_valid = true;
+    if ((rc = mark_done(ctx, sc))) return rc;
     GS_CUDA(cudaStreamSynchronize(sc));
     return GS_OK;
 }

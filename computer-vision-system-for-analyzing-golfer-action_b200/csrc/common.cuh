@@ -124,6 +124,13 @@ struct Ctx {
     cudaStream_t own_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
     bool ev_valid = false;
+    // Every entry point shares this context's workspace, whatever stream it runs on: each call records
+    // `ev_last` behind its work and the next call's stream(s) wait for it first, so sequential calls from
+    // one thread on different streams (a device call on the caller's stream, then a host call on the
+    // context's own streams) never overlap on the workspace.
+    cudaEvent_t ev_last = nullptr;
+    bool ev_last_valid = false;
+    cudaStream_t last_stream = nullptr;
 
     Bf16Path *bf16 = nullptr;
     Profiler prof;
@@ -158,6 +165,11 @@ struct LaunchScope {
         if (slot >= 0) cudaEventRecord(c->prof.pool[slot].e1, st);
     }
 };
+
+// api.cu: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query are made once per
+// (device, kernel) and remembered, not repeated on every call of an entry point
+int ensure_dyn_smem(Ctx *ctx, const void *kernel, size_t bytes);
+int cached_occupancy(Ctx *ctx, const void *kernel, int nthreads, size_t smem_bytes, int *blocks_per_sm);
 
 // align.cu
 int align_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,

@@ -317,6 +317,16 @@ def _current_device(torch, t=None) -> int:
     return torch.cuda.current_device()
 
 
+def _dev_tensor(torch, t, name: str, dev: int, dtype):
+    """`t` as a contiguous tensor of `dtype` on cuda:`dev`; anything else raises instead of handing a kernel a
+    host or foreign-device pointer."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise GolferError(f"{name} must be a CUDA tensor")
+    if t.device.index != dev:
+        raise GolferError(f"{name} is on cuda:{t.device.index}, expected cuda:{dev} (all tensors of one call share a device)")
+    return t.to(dtype).contiguous()
+
+
 def segment(skel, precision: str = "bf16", cfg: GolfSegConfig = V0, seed: int = 1234):
     """Module-level convenience: seeded random-init weights (the reference ships none)."""
     torch = _torch()
@@ -325,9 +335,12 @@ def segment(skel, precision: str = "bf16", cfg: GolfSegConfig = V0, seed: int = 
     key = (dev, precision, cfg.config_hash(), seed)
     seg = _default_segmenters.get(key)
     if seg is None or seg.max_B < B or seg.max_T < T:
+        # grow-only: alternating shapes must not rebuild the workspace on every call
+        nB, nT = max(B, 1), max(T, 1)
         if seg is not None:
+            nB, nT = max(nB, seg.max_B), max(nT, seg.max_T)
             seg.ctx.close()
-        seg = Segmenter(cfg, None, seed, precision, dev, max(B, 1), max(T, 1))
+        seg = Segmenter(cfg, None, seed, precision, dev, nB, nT)
         _default_segmenters[key] = seg
     return seg.segment(skel)
 
@@ -346,7 +359,7 @@ def align_batch(a, b, ctx: Optional[Context] = None, want_path: bool = True):
     on_dev = isinstance(a, torch.Tensor) and a.is_cuda
     if on_dev:
         a = a.contiguous().float()
-        b = b.contiguous().float()
+        b = _dev_tensor(torch, b, "b", a.device.index, torch.float32)
     else:
         was_numpy = not isinstance(a, torch.Tensor)
         a = torch.as_tensor(np.asarray(a) if was_numpy else a, dtype=torch.float32).contiguous()
@@ -399,11 +412,14 @@ def align(a, b):
 def pair_cost(a, b, ctx: Optional[Context] = None):
     """Cost matrices only: a [N,Ta,V,Cc], b [N,Tb,V,Cc] (CUDA tensors) -> [N,Ta,Tb] fp32."""
     torch = _torch()
-    a = a.contiguous().float()
-    b = b.contiguous().float()
+    dev = _current_device(torch, a)
+    a = _dev_tensor(torch, a, "a", dev, torch.float32)
+    b = _dev_tensor(torch, b, "b", dev, torch.float32)
+    if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise GolferError(f"pair_cost expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
     N, Ta, V, Cc = (int(s) for s in a.shape)
     Tb = int(b.shape[1])
-    ctx = ctx or _align_ctx(_current_device(torch, a))
+    ctx = ctx or _align_ctx(dev)
     out = torch.empty((N, Ta, Tb), dtype=torch.float32, device=a.device)
     if N:
         _check(ctx._L.gs_pair_cost(ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc,
@@ -415,15 +431,30 @@ def compare(a, b, path, path_len, ctx: Optional[Context] = None):
     """"Compare 2 skeleton" (README.md:50-52): per aligned step, per joint distance.
     a [N,Ta,V,Cc], b [N,Tb,V,Cc], path [N,Ta+Tb-1,2], path_len [N] (CUDA) -> [N,Ta+Tb-1,V] fp32."""
     torch = _torch()
-    a = a.contiguous().float()
-    b = b.contiguous().float()
+    dev = _current_device(torch, a)
+    a = _dev_tensor(torch, a, "a", dev, torch.float32)
+    b = _dev_tensor(torch, b, "b", dev, torch.float32)
+    if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise GolferError(f"compare expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
     N, Ta, V, Cc = (int(s) for s in a.shape)
     Tb = int(b.shape[1])
-    ctx = ctx or _align_ctx(_current_device(torch, a))
+    path = _dev_tensor(torch, path, "path", dev, torch.int32)              # int64 paths are converted, not reinterpreted
+    path_len = _dev_tensor(torch, path_len, "path_len", dev, torch.int32)
+    if tuple(path.shape) != (N, Ta + Tb - 1, 2) or tuple(path_len.shape) != (N,):
+        raise GolferError(f"path must be [N,Ta+Tb-1,2] and path_len [N]; got {tuple(path.shape)} {tuple(path_len.shape)}")
+    if N:
+        # the kernel indexes a and b with the path entries: reject anything outside the two sequences
+        L = path_len.clamp(min=0).to(torch.int64)
+        live = torch.arange(Ta + Tb - 1, device=path.device)[None, :] < L[:, None]
+        bad = (path_len < 1) | (path_len > Ta + Tb - 1)
+        oob = live & ((path[..., 0] < 0) | (path[..., 0] >= Ta) | (path[..., 1] < 0) | (path[..., 1] >= Tb))
+        if bool(bad.any()) or bool(oob.any()):
+            raise GolferError("compare: path / path_len hold entries outside the two sequences")
+    ctx = ctx or _align_ctx(dev)
     out = torch.empty((N, Ta + Tb - 1, V), dtype=torch.float32, device=a.device)
     if N:
-        _check(ctx._L.gs_compare(ctx.handle, a.data_ptr(), b.data_ptr(), path.contiguous().data_ptr(),
-                                 path_len.contiguous().data_ptr(), N, Ta, Tb, V, Cc, out.data_ptr(),
+        _check(ctx._L.gs_compare(ctx.handle, a.data_ptr(), b.data_ptr(), path.data_ptr(),
+                                 path_len.data_ptr(), N, Ta, Tb, V, Cc, out.data_ptr(),
                                  _stream_ptr(torch)), "gs_compare")
     return out
 
@@ -472,8 +503,9 @@ def align_phase(a, b, labels_a, labels_b, penalty: float, ctx: Optional[Context]
     for t in (a, b, labels_a, labels_b):
         if not (isinstance(t, torch.Tensor) and t.is_cuda):
             raise GolferError("align_phase takes device tensors")
-    a = a.contiguous().float()
-    b = b.contiguous().float()
+    dev = a.device.index
+    a = _dev_tensor(torch, a, "a", dev, torch.float32)
+    b = _dev_tensor(torch, b, "b", dev, torch.float32)
     if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
         raise GolferError(f"align_phase expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
     N, Ta, V, Cc = (int(x) for x in a.shape)
@@ -482,9 +514,8 @@ def align_phase(a, b, labels_a, labels_b, penalty: float, ctx: Optional[Context]
         raise GolferError(f"labels must be [N,Ta] and [N,Tb]; got {tuple(labels_a.shape)} {tuple(labels_b.shape)}")
     if Cc < 2 or Ta < 1 or Tb < 1:
         raise GolferError("align_phase needs (x, y) channels and at least one frame per sequence")
-    la = labels_a.to(torch.uint8).contiguous()
-    lb = labels_b.to(torch.uint8).contiguous()
-    dev = _current_device(torch, a)
+    la = _dev_tensor(torch, labels_a, "labels_a", dev, torch.uint8)
+    lb = _dev_tensor(torch, labels_b, "labels_b", dev, torch.uint8)
     ctx = ctx or _align_ctx(dev)
     maxL = Ta + Tb - 1
     cost = torch.empty((N,), dtype=torch.float32, device=a.device)

@@ -220,3 +220,105 @@ def test_four_byte_aligned_inputs():
     ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 4)
     cost, path, plen = golfer_b200.host.align_batch(va, vb)
     _check_against(a, b, cost, path, plen, ref_cost, ref_path, ref_plen)
+
+
+# ---- non-finite values on the boundary (row 0 steps LEFT, column 0 steps UP whatever D holds) ----------
+@pytest.mark.parametrize("N,Ta,Tb,V", [(5, 6, 4, 17), (5, 4, 6, 17), (4, 70, 41, 17), (4, 41, 70, 17), (3, 300, 257, 17),
+                                       (3, 257, 300, 17), (3, 9, 5, 25), (3, 5, 9, 25), (2, 1, 7, 17), (2, 7, 1, 17)])
+def test_infinite_penalty_with_mismatched_first_labels(N, Ta, Tb, V):
+    """penalty = +inf and la[:,0] != lb[:,0]: D[0,0] = inf, so every D is inf and every comparison of the DP
+    step is false; the path must still be the oracle's (forced LEFT on row 0, UP on column 0, DIAG inside)."""
+    a, b = oalign.synth_swings(N, Ta, Tb, V=V, seed=Ta * 3 + Tb)
+    la = np.zeros((N, Ta), np.uint8)
+    lb = np.ones((N, Tb), np.uint8)
+    la[0::2, Ta // 2:] = 1                       # some pairs agree further in; the first frames never do
+    ref_cost, ref_path, ref_plen = align_native.align_phase_batch_c(a, b, la, lb, float("inf"), 2)
+    cost, path, plen = golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(lb), float("inf"))
+    assert np.array_equal(cost.cpu().numpy(), ref_cost)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+
+
+@pytest.mark.parametrize("N,Ta,Tb,V", [(6, 6, 4, 17), (6, 4, 6, 17), (6, 90, 61, 17), (6, 61, 90, 17), (6, 12, 7, 25),
+                                       (6, 7, 12, 25), (6, 40, 1100, 17)])
+def test_nan_and_inf_keypoints_rectangular(N, Ta, Tb, V):
+    """NaN / inf keypoints on and off the boundary with Ta != Tb, on the pipelined kernel (both orientations)
+    and the generic kernel (V != 17, more than 1024 columns)."""
+    a, b = oalign.synth_swings(N, Ta, Tb, V=V, seed=Ta * 11 + Tb)
+    a[0, 0, 0, 0] = np.nan                       # first student frame: the whole first row is NaN
+    b[1, 0, 2, 1] = np.inf                       # first reference frame: the whole first column is inf
+    a[2, Ta - 1, 1, 0] = np.nan                  # last row
+    b[3, Tb // 2, 0, 0] = -np.inf                # an interior column
+    a[4, :, 3, 1] = np.nan                       # everything NaN
+    with np.errstate(over="ignore", invalid="ignore"):
+        ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 2)
+    cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    torch.cuda.synchronize()
+    assert np.array_equal(cost.cpu().numpy(), ref_cost, equal_nan=True)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+
+
+@pytest.mark.parametrize("N,Ta,Tb,pen", [(5, 257, 300, 2.0), (4, 1, 33, 1.0), (700, 31, 40, 0.75), (3, 1, 2, 1.5),
+                                         (4, 33, 65, 0.25), (2, 1000, 1024, 0.5)])
+def test_phase_alignment_shorter_student(N, Ta, Tb, pen):
+    """Ta < Tb with phase labels: same pipelined kernel, sequences exchanged inside the launch."""
+    a, b = oalign.synth_swings(N, Ta, Tb, seed=Ta * 5 + Tb)
+    la, lb = _phase_labels(N, Ta, 3), _phase_labels(N, Tb, 4)
+    ref_cost, ref_path, ref_plen = align_native.align_phase_batch_c(a, b, la, lb, pen, 4)
+    cost, path, plen = golfer_b200.align_phase(_dev(a), _dev(b), _dev(la), _dev(lb), pen)
+    assert np.array_equal(cost.cpu().numpy(), ref_cost)
+    assert np.array_equal(plen.cpu().numpy(), ref_plen)
+    assert np.array_equal(path.cpu().numpy(), ref_path)
+
+
+def test_ties_resolve_identically_in_both_orientations():
+    """Quantised keypoints make exact ties between up / left / diagonal common: the exchanged-sequence launch
+    (Ta < Tb) must break them exactly as the oracle does in the original orientation."""
+    rng = np.random.default_rng(5)
+    for Ta, Tb in ((40, 64), (64, 40), (33, 34), (34, 33)):
+        a = rng.integers(0, 3, (16, Ta, 17, 2)).astype(np.float32)
+        b = rng.integers(0, 3, (16, Tb, 17, 2)).astype(np.float32)
+        ref_cost, ref_path, ref_plen = align_native.align_batch_c(a, b, 2)
+        cost, path, plen = golfer_b200.host.align_batch(_dev(a), _dev(b))
+        _check_against(a, b, cost, path, plen, ref_cost, ref_path, ref_plen)
+
+
+def test_device_call_then_host_call_share_workspace_safely():
+    """A device-stream call followed at once by a host-buffer call on the same context (its own streams):
+    the second must wait for the first (ctx ordering event), results equal the oracle's."""
+    a, b = oalign.synth_swings(600, 120, 100, seed=31)
+    a2, b2 = oalign.synth_swings(600, 120, 100, seed=32)
+    rc1, rp1, _ = align_native.align_batch_c(a, b, 4)
+    rc2, rp2, _ = align_native.align_batch_c(a2, b2, 4)
+    ctx = golfer_b200.host.Context(0)
+    side = torch.cuda.Stream()
+    da, db = _dev(a), _dev(b)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            c1, p1, _ = golfer_b200.host.align_batch(da, db, ctx=ctx)
+        c2, p2, _ = golfer_b200.host.align_batch(a2, b2, ctx=ctx)          # host entry point, own streams
+        torch.cuda.synchronize()
+        assert np.array_equal(c1.cpu().numpy(), rc1) and np.array_equal(p1.cpu().numpy(), rp1)
+        assert np.array_equal(c2.numpy(), rc2) and np.array_equal(p2.numpy(), rp2)
+    ctx.close()
+
+
+def test_compare_validates_devices_dtypes_and_path_range():
+    a, b = oalign.synth_swings(2, 12, 9, seed=6)
+    da, db = _dev(a), _dev(b)
+    cost, path, plen = golfer_b200.host.align_batch(da, db)
+    want = golfer_b200.compare(da, db, path, plen)
+    got = golfer_b200.compare(da, db, path.to(torch.int64), plen.to(torch.int64))   # converted, not reinterpreted
+    assert torch.equal(got, want)
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.compare(da, torch.from_numpy(b), path, plen)                    # host tensor
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.host.align_batch(da, torch.from_numpy(b))
+    bad = path.clone()
+    bad[0, 0, 0] = 12                                                                # past the end of a
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.compare(da, db, bad, plen)
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.compare(da, db, path, plen + 100)
