@@ -37,7 +37,7 @@
 // brought by TMA); a box is released after its three MMA1s (chunk order: box-major, partition
 // minor), so the next tile's boxes load and get gated while this tile is still in the MMAs.
 #pragma once
-#include "tc_gemm.cuh"
+#include "umma.cuh"
 
 namespace gs {
 namespace gcn {
@@ -62,7 +62,8 @@ struct Params {
     int Cin, C, T, B;
     int mtiles, ntiles, rows_per_clip;
     int xslots, wstages, eslots, nacc;
-    int rev;              // 1: walk the tiles from the last clip down (the tail of the previous block's U is in L2)
+    int store_xg;         // 1: the gated input is stored (the next kernel's residual projection reads it); 0: identity
+                          //    blocks re-gate the previous block's output themselves (tcn_fused.cuh)
     const float *gT;      // [B,T,Cin]   (maps carry the data; non-null = gating on)
     const float *gV;      // [B,17,Cin]
     const float *A;       // [3,17,17] fp32
@@ -102,16 +103,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
 // MN-major (channels contiguous) SW128 operand: rows of the K dimension are 128 B apart, 8-row groups
 // 1024 B apart (SBO); LBO = distance between 64-element MN blocks (unused here: N = 64 = one block).
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
@@ -150,10 +141,6 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
         : "=f"(d.x), "=f"(d.y)
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&v);
 }
 
 __global__ void __launch_bounds__(kThreadsGcn, 1)
@@ -255,7 +242,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         int slot = 0, tcount = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int tl = tile;
             const int b = tl / prm.mtiles;
             const int mt = tl % prm.mtiles;
             const int row0 = mt * kRowsPerTile;
@@ -403,7 +390,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int tl = tile;
             const int b = tl / prm.mtiles;
             const int row0 = (tl % prm.mtiles) * kRowsPerTile;
             for (int cb = 0; cb < nbc; ++cb) {
@@ -450,15 +437,19 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 if (leader) {
                     mbar_arrive(&x_ready[slot]);
                     GCN_TRACE(3, tcount, 16 + cb);
-                    tma_store_3d(&mapXg, sl, cb * 64, row0, b);
-                    tma_store_commit();
-                    // the PREVIOUS box's store has been in flight for a whole box period: drain it now
-                    // and release its slot (deferred wait keeps the gate pipeline moving)
-                    if (prev_slot >= 0) {
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        mbar_arrive(&x_empty[prev_slot]);
+                    if (prm.store_xg) {
+                        tma_store_3d(&mapXg, sl, cb * 64, row0, b);
+                        tma_store_commit();
+                        // the PREVIOUS box's store has been in flight for a whole box period: drain it now
+                        // and release its slot (deferred wait keeps the gate pipeline moving)
+                        if (prev_slot >= 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            mbar_arrive(&x_empty[prev_slot]);
+                        }
+                        prev_slot = slot;
+                    } else {
+                        mbar_arrive(&x_empty[slot]);     // nothing reads the box but the MMA1s
                     }
-                    prev_slot = slot;
                 }
                 if (++slot == XS) { slot = 0; ph ^= 1; }
             }
@@ -477,9 +468,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         uint32_t acc_cnt = 0, ecnt = 0;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int tl = prm.rev ? prm.ntiles - 1 - tile : tile;
+            const int tl = tile;
             const int b = tl / prm.mtiles;
-            const int row0 = (tl % prm.mtiles) * kRowsPerTile;
+            const int mt = tl % prm.mtiles;
             const uint32_t as = acc_cnt % (uint32_t)NACC, aph = (acc_cnt / (uint32_t)NACC) & 1;
             mbar_wait(&acc_full[as], aph);
             if (leader) GCN_TRACE(4, tcount, 0);
@@ -523,7 +514,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     fence_proxy_async_smem();
                     asm volatile("bar.sync 1, 512;" ::: "memory");
                     if (leader) {
-                        tma_store_3d(&mapY, smem + lay.epi_off + es * 16384u, qb * 64, row0, b);
+                        // Y is stored JOINT-MAJOR [B,V,T,C] through a (C,V,T,B) map with a (64,17,7,1) box: the staged
+                        // rows (frame, joint) land transposed for free (tcn_fused.cuh reads frame windows per joint)
+                        tma_store_4d(&mapY, smem + lay.epi_off + es * 16384u, qb * 64, 0, mt * kFramesPerTile, b);
                         tma_store_commit();
                     }
                     ++ecnt;
@@ -552,16 +545,12 @@ struct LaunchGcn {
 // stream), then as many input boxes as remain (at least 3).
 inline bool plan_smem(Params &p) {
     p.nacc = (2 * p.C <= 256) ? 2 : 1;
-    static const int env_ws = getenv("GOLFER_GCN_WS") ? atoi(getenv("GOLFER_GCN_WS")) : 0;
-    static const int env_es = getenv("GOLFER_GCN_ES") ? atoi(getenv("GOLFER_GCN_ES")) : 0;
     const int es_c[2] = {2, 1};
     const int ws_c[3] = {4, 3, 2};
     // two staging slots first (measured: the store of box n draining behind box n+1 is worth more than a
     // deeper weight ring), then the deepest weight ring, then as many input boxes as remain
     for (int es : es_c) {
-        if (env_es && es != env_es) continue;
         for (int ws : ws_c) {
-            if (env_ws && ws != env_ws) continue;
             for (int xs = kMaxXSlots; xs >= 3; --xs) {
                 if (smem_layout(p.C, xs, ws, es).total <= 227u * 1024u) {
                     p.xslots = xs;
@@ -583,7 +572,8 @@ inline int launch(Ctx *ctx, int kid, LaunchGcn &L, cudaStream_t st) {
     const Smem lay = smem_layout(L.prm.C, L.prm.xslots, L.prm.wstages, L.prm.eslots);
     int grid = L.prm.ntiles < ctx->sm_count ? L.prm.ntiles : ctx->sm_count;
     if (grid < 1) return GS_OK;
-    GS_CUDA(cudaFuncSetAttribute(gcn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    int rc = ensure_dyn_smem(ctx, (const void *)gcn_fused_kernel, lay.total);
+    if (rc != GS_OK) return rc;
     {
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
         gcn_fused_kernel<<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT, L.mapGV,

@@ -1,31 +1,28 @@
 // bf16 throughput path of the segmentation network: bf16 activations in HBM, every dense
-// contraction on tcgen05 tensor cores (tc_gemm.cuh) with fp32 accumulation in TMEM.
+// contraction on tcgen05 tensor cores with fp32 accumulation in TMEM.
 //
-// Per block i >= 1 (block 0 has Cin = 3 and runs its tiny K=9 / K=3 contractions in
-// `front_kernel` on CUDA cores):
-//   aggregate   U_{i-1} * gates -> Xg [rows,Cin], XA [rows,3Cin]            (CUDA cores, fp32 math)
-//   tc_gemm     Y = relu(XA . Wg + bg)                                       (K = 3Cin, N = C)
-//   tc_gemm     H = relu(Y . W1 + b1)                                        (K = C,    N = C)
-//   tc_gemm     U = relu(sum_{r,j} shift_{(j-1)d_r}(H_r) . W2[r,j] + Xg . Wr + b)   (taps + residual)
-//   stats / se / stj (segment_common.cuh)                                    -> gates for block i+1
-// Rounding points (mirrored by oracle/segnet_bf16.py): weights, Xg, XA, Y, H, U (and block 0's
-// residual projection) are rounded to bf16; everything else is fp32.
+// Block 0 (Cin = 3):  front_mma_kernel   input BN + adjacency on CUDA cores, the K=9 mix and the K=3
+//                                        residual projection as one TF32 mma.sync GEMM -> Y (joint-major), R0
+// Block i >= 1:       gcn_fused_kernel   gate-on-load, adjacency contraction + channel mix -> Y (joint-major)
+//                                        (+ the gated input Xg for the residual)
+// every block:        tcn_fused_kernel   branch 1x1 + dilated taps + residual + ReLU -> U, pooling sums
+//                     se_kernel, stj_tc_kernel (segment_common.cuh) -> gates applied by the NEXT reader of U
+// XA (3x the input) and H (the branch 1x1 output) never reach HBM.  Rounding points: weights, Xg, XA, Y,
+// H, U (and block 0's residual projection) are rounded to bf16; everything else is fp32.
 //
 // Stages replaced: /root/reference/README.md:27-34.
 #include "segment_common.cuh"
-#include "tc_gemm.cuh"
+#include "umma.cuh"
 #include "gcn_fused.cuh"
-#include "tconv_window.cuh"
+#include "tcn_fused.cuh"
 #include <stdlib.h>
 
 namespace gs {
 
 struct BlockMaps {
-    CUtensorMap xa_in, y_out, y_in;
-    CUtensorMap h_out_jm;                                        // 1x1 GEMM store into joint-major H [B,V,T,C]
-    tw::Maps tw;                                                 // sliding-window temporal conv
+    tf::Maps tf;                                                 // fused temporal kernel
     CUtensorMap f_x_load, f_xg_store, f_y_store, f_gt, f_gv;    // fused GCN kernel (7-frame tiles)
-    CUtensorMap wg, w1;
+    CUtensorMap wg;
 };
 
 struct Bf16Path {
@@ -35,127 +32,17 @@ struct Bf16Path {
     float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
     std::vector<BlockMaps> maps;
     int maps_T = -1;
-    bool stj_tc = true;         // GOLFER_STJ_FFMA=1 keeps the exact-fp32 FFMA ST-joint kernel
-    bool fused_gcn = true;      // GOLFER_GCN_UNFUSED=1 selects the SIMT-aggregate + dense-GEMM pair
-    bool debug_xa = false;      // GOLFER_DEBUG_XA=1 dumps the fused kernel's XA chunks into bufXA
-    unsigned long long *trace = nullptr;   // GOLFER_TRACE_GCN=1: [blocks][5 roles][6 tiles][64 events] clock64
-    unsigned long long *trace_tc = nullptr;   // GOLFER_TRACE_TC=1: [blocks][2 kernels][5 roles][8 tiles][32 events]
+    bool debug_xa = false;      // GOLFER_DEBUG_XA=1: the fused GCN kernel also dumps its XA chunks into bufXA (tests/test_gpu_kernels.py)
+    unsigned long long *trace = nullptr;   // GOLFER_TRACE_GCN=1: [blocks][5 roles][6 tiles][64 events] clock64 (tools/trace_gcn.py)
+    unsigned long long *trace_tcn = nullptr;   // GOLFER_TRACE_TCN=1: [blocks][4 roles][8 steps][16 events] (tools/trace_tcn.py)
 };
 
 namespace {
 
-// ---- block 0 on CUDA cores: input BN + adjacency + K=9 mix (+ReLU) and K=3 residual ------
-// One CTA = kFrontFrames frames.  Phase 3 work unit = (row, 4 output channels): the row's 3*Cin
-// aggregated inputs and Cin raw inputs against the thread's weight columns held in registers,
-// packed to two 8-byte bf16 stores (Y and the residual projection R0); a warp writes 256
-// contiguous bytes of each.  C/4 must divide 256.
 constexpr int kFrontFrames = 16;
 
-struct FrontSmem {
-    int a, w, bias, x, xa, total;   // float offsets
-};
-__host__ __device__ inline FrontSmem front_smem(int Cin, int C) {
-    FrontSmem s;
-    s.a = 0;
-    s.w = s.a + 3 * V17 * V17 + 1;
-    s.bias = s.w;
-    s.x = s.bias;
-    s.xa = s.x + kFrontFrames * V17 * Cin;
-    s.total = s.xa + kFrontFrames * V17 * 3 * Cin;
-    return s;
-}
-
-template <int CIN>
-__global__ void __launch_bounds__(256)
-front_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale, const float *__restrict__ in_shift,
-             const float *__restrict__ A, const float *__restrict__ Wg, const float *__restrict__ bg,
-             const float *__restrict__ Wr, const float *__restrict__ br, int C, size_t nframes,
-             __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ R0) {
-    extern __shared__ __align__(16) float sm[];
-    constexpr int K3 = 3 * CIN;
-    const FrontSmem lay = front_smem(CIN, C);
-    float *sA = sm + lay.a, *sx = sm + lay.x, *sxa = sm + lay.xa;
-    for (int k = threadIdx.x; k < 3 * V17 * V17; k += blockDim.x) sA[k] = A[k];
-    const size_t f0 = (size_t)blockIdx.x * kFrontFrames;
-    const int nf = (int)(nframes - f0 < (size_t)kFrontFrames ? nframes - f0 : (size_t)kFrontFrames);
-    for (int e = threadIdx.x; e < nf * V17 * CIN; e += blockDim.x) {
-        const int vc = e % (V17 * CIN);
-        sx[e] = skel[f0 * V17 * CIN + e] * in_scale[vc] + in_shift[vc];
-    }
-    // this thread's 4 output channels never change (C/4 divides the block size): weights in registers
-    const int ng = C / 4;
-    const int c0 = (threadIdx.x % ng) * 4;
-    float wreg[K3 + CIN][4], breg[2][4];
-#pragma unroll
-    for (int k = 0; k < K3 + CIN; ++k) {
-        const float *src = k < K3 ? Wg + (size_t)k * C + c0 : Wr + (size_t)(k - K3) * C + c0;
-        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src));
-        wreg[k][0] = w0.x; wreg[k][1] = w0.y; wreg[k][2] = w0.z; wreg[k][3] = w0.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        breg[0][e] = bg[c0 + e];
-        breg[1][e] = br[c0 + e];
-    }
-    __syncthreads();
-    // adjacency contraction: unit = (frame, output joint w) -> the 3*CIN aggregated inputs of that row
-    for (int u = threadIdx.x; u < nf * V17; u += blockDim.x) {
-        const int f = u / V17, w = u - f * V17;
-        float acc[K3];
-#pragma unroll
-        for (int k = 0; k < K3; ++k) acc[k] = 0.f;
-        const float *xf = sx + f * V17 * CIN;
-#pragma unroll
-        for (int v = 0; v < V17; ++v) {
-            float x[CIN];
-#pragma unroll
-            for (int c = 0; c < CIN; ++c) x[c] = xf[v * CIN + c];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const float a = sA[(p * V17 + w) * V17 + v];
-#pragma unroll
-                for (int c = 0; c < CIN; ++c) acc[p * CIN + c] += a * x[c];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K3; ++k) sxa[u * K3 + k] = acc[k];
-    }
-    __syncthreads();
-    for (int u = threadIdx.x; u < nf * V17 * ng; u += blockDim.x) {
-        const int row = u / ng;
-        float y[4], r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            y[e] = breg[0][e];
-            r[e] = breg[1][e];
-        }
-#pragma unroll
-        for (int k = 0; k < K3; ++k) {
-            const float a = sxa[row * K3 + k];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) y[e] += a * wreg[k][e];
-        }
-#pragma unroll
-        for (int c = 0; c < CIN; ++c) {
-            const float a = sx[row * CIN + c];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] += a * wreg[K3 + c][e];
-        }
-        uint2 py, pr;
-        __nv_bfloat162 *hy = reinterpret_cast<__nv_bfloat162 *>(&py), *hr = reinterpret_cast<__nv_bfloat162 *>(&pr);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            hy[e] = __floats2bfloat162_rn(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f));
-            hr[e] = __floats2bfloat162_rn(r[2 * e], r[2 * e + 1]);
-        }
-        const size_t o = (f0 * V17 + row) * C + c0;
-        *reinterpret_cast<uint2 *>(Y + o) = py;
-        *reinterpret_cast<uint2 *>(R0 + o) = pr;
-    }
-}
-
 // ---- block 0 with the two K = 9 / K = 3 mixes on warp-level tensor cores ---------------------------
-// The CUDA-core form above is bound by FMA issue (12 x 2C FMAs per row; 0.15 ms against a 0.054 ms
+// A CUDA-core form is bound by FMA issue (12 x 2C FMAs per row; 0.15 ms against a 0.054 ms
 // write floor).  Here a row's inputs form one 16-wide A row
 //     [ 9 aggregated inputs | 3 normalised raw inputs | 1 | 0 0 0 ]
 // and BOTH outputs come from one [16 x 2C] matrix (host: pack_front_matrix)
@@ -180,10 +67,11 @@ __device__ __forceinline__ void quad_transpose(uint32_t (&p)[4], int q) {
     if (hi) { p[0] = s0; p[1] = s1; } else { p[2] = s0; p[3] = s1; }
 }
 
+// Y is written JOINT-MAJOR [B,V,T,C] (tcn_fused.cuh reads frame windows per joint), R0 frame-major [B,T,V,C].
 template <int CIN>
 __global__ void __launch_bounds__(256)
 front_mma_kernel(const float *__restrict__ skel, const float *__restrict__ in_scale, const float *__restrict__ in_shift,
-                 const float *__restrict__ A, const float *__restrict__ Bm, int C, size_t nframes,
+                 const float *__restrict__ A, const float *__restrict__ Bm, int C, int T, size_t nframes,
                  __nv_bfloat16 *__restrict__ Y, __nv_bfloat16 *__restrict__ R0) {
     static_assert(CIN == 3, "A-row layout assumes 3 input channels");
     extern __shared__ __align__(16) float sm[];
@@ -262,7 +150,6 @@ front_mma_kernel(const float *__restrict__ skel, const float *__restrict__ in_sc
 #pragma unroll
             for (int t = 0; t < 4; ++t) mma_tf32(acc[t], a0, a1, a2, a3, bf[ks][t][0], bf[ks][t][1]);
         }
-        const size_t g0 = (f0 * V17 + r0) * C, g1 = (f0 * V17 + r1) * C;
         const bool v0 = r0 < nf * V17, v1 = r1 < nf * V17;
         // pack, then transpose 4x4 inside the quad so that lane tg ends with the 8 columns of n-tile tg:
         // one 16-byte store per lane and row (a quad writes 64 contiguous bytes) instead of four 4-byte ones
@@ -271,14 +158,21 @@ front_mma_kernel(const float *__restrict__ skel, const float *__restrict__ in_sc
         for (int t = 0; t < 4; ++t) {
             float y0 = acc[t][0], y1 = acc[t][1], y2 = acc[t][2], y3 = acc[t][3];
             if (is_y) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
-            p0[t] = gcn::pack_bf16(y0, y1);
-            p1[t] = gcn::pack_bf16(y2, y3);
+            p0[t] = tc::pack_bf16(y0, y1);
+            p1[t] = tc::pack_bf16(y2, y3);
         }
         quad_transpose(p0, tg);
         quad_transpose(p1, tg);
         const int col = cbase + tg * 8;
-        if (v0) *reinterpret_cast<uint4 *>(dst + g0 + col) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-        if (v1) *reinterpret_cast<uint4 *>(dst + g1 + col) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+        // destination row: frame-major (f*17 + v) for R0, joint-major ((b*17 + v)*T + t) for Y
+        auto dst_row = [&](int r) -> size_t {
+            const size_t f = f0 + (size_t)(r / V17);
+            if (!is_y) return f * V17 + (size_t)(r % V17);
+            const size_t b = f / (size_t)T, t = f - b * (size_t)T;
+            return (b * V17 + (size_t)(r % V17)) * (size_t)T + t;
+        };
+        if (v0) *reinterpret_cast<uint4 *>(dst + dst_row(r0) * C + col) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+        if (v1) *reinterpret_cast<uint4 *>(dst + dst_row(r1) * C + col) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
     }
 }
 
@@ -308,46 +202,40 @@ int upload_bf16(Ctx *ctx, const std::vector<__nv_bfloat16> &h, __nv_bfloat16 **d
     GS_CUDA(cudaMemcpy(*d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
     return GS_OK;
 }
-
 int build_maps(Ctx *ctx, int T) {
     Bf16Path *bp = ctx->bf16;
     if (bp->maps_T == T) return GS_OK;
     const int rows = T * V17, batch = ctx->max_B;
     const int R = ctx->cfg.num_branches;
     bp->maps.assign(ctx->blocks.size(), BlockMaps{});
+    int dmax = 1;
+    for (int r = 0; r < R; ++r) dmax = dmax > ctx->cfg.dilations[r] ? dmax : ctx->cfg.dilations[r];
+    const int nout = tf::kWin - 2 * dmax;
     int rc;
     for (size_t i = 0; i < ctx->blocks.size(); ++i) {
         const BlockParams &b = ctx->blocks[i];
         BlockMaps &m = bp->maps[i];
         const int C = b.c, cin = b.cin, cr = b.cr;
-        if ((rc = tc::make_act_map(&m.y_out, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
-        if ((rc = tc::make_act_map(&m.y_in, ctx->bufY, C, rows, batch, 64, tc::kTileM))) return rc;
-        const int crm = cr < 16 ? 16 : cr;      // MMA width of a branch tap (tconv_window.cuh)
-        {   // temporal conv: joint-major H, window loads, (C,V,T,B) views of the [B,T,V,C] tensors
-            int dmax = 1;
-            for (int r = 0; r < R; ++r) dmax = dmax > ctx->cfg.dilations[r] ? dmax : ctx->cfg.dilations[r];
-            const bool proj = (i > 0 && b.has_res);
-            if ((rc = tw::make_bvtc_map(&m.h_out_jm, ctx->bufH, C, T, batch, true, 64, gcn::kFramesPerTile))) return rc;
-            if ((rc = tw::make_bvtc_map(&m.tw.h_win, ctx->bufH, C, T, batch, false, 64, tw::kFramesTile + 2 * dmax))) return rc;
-            if ((rc = tw::make_btvc_joint_map(&m.tw.out, ctx->bufU[i & 1], C, T, batch, 64, tw::kFramesTile))) return rc;
-            // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
-            if ((rc = tw::make_btvc_joint_map(&m.tw.res, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, tw::kFramesTile)))
-                return rc;
-            m.tw.xg = m.tw.res;
-            if ((rc = tc::make_weight_map(&m.tw.w2, bp->W2p[i], crm, R * 3 * crm, crm, crm))) return rc;
-            m.tw.wr = m.tw.w2;
-            if (proj) {
-                if ((rc = tw::make_btvc_joint_map(&m.tw.xg, ctx->bufX, cin, T, batch, 64, tw::kFramesTile))) return rc;
-                if ((rc = tc::make_weight_map(&m.tw.wr, bp->WrT[i], cin, C, 64, 64))) return rc;
-            }
+        const int crm = cr < 16 ? 16 : cr;      // MMA width of a branch tap (tcn_fused.cuh)
+        const bool proj = (i > 0 && b.has_res);
+        // temporal kernel: joint-major Y windows, (C,V,T,B) views of the [B,T,V,C] tensors
+        if ((rc = tf::make_bvtc_map(&m.tf.y_win, ctx->bufY, C, T, batch, false, 64, tf::kWin))) return rc;
+        if ((rc = tf::make_btvc_joint_map(&m.tf.out, ctx->bufU[i & 1], C, T, batch, 64, nout))) return rc;
+        // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
+        if ((rc = tf::make_btvc_joint_map(&m.tf.res, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, nout))) return rc;
+        if ((rc = tc::make_weight_map(&m.tf.w1, bp->W1T[i], C, C, 64, 64))) return rc;
+        if ((rc = tc::make_weight_map(&m.tf.w2, bp->W2p[i], crm, R * 3 * crm, crm, crm))) return rc;
+        m.tf.xg = m.tf.res;
+        m.tf.wr = m.tf.w1;
+        if (proj) {
+            if ((rc = tf::make_btvc_joint_map(&m.tf.xg, ctx->bufX, cin, T, batch, 64, tf::kWin))) return rc;
+            if ((rc = tc::make_weight_map(&m.tf.wr, bp->WrT[i], cin, C, 64, 64))) return rc;
         }
-        if ((rc = tc::make_weight_map(&m.w1, bp->W1T[i], C, C, 64, C))) return rc;
         if (i > 0) {
-            if ((rc = tc::make_act_map(&m.xa_in, ctx->bufXA, 3 * cin, rows, batch, 64, tc::kTileM))) return rc;
             if ((rc = tc::make_weight_map(&m.wg, bp->WgT[i], 3 * cin, C, 64, C))) return rc;
             if ((rc = tc::make_act_map(&m.f_x_load, ctx->bufU[(i - 1) & 1], cin, rows, batch, 64, tc::kTileM))) return rc;
             if ((rc = tc::make_act_map(&m.f_xg_store, ctx->bufX, cin, rows, batch, 64, gcn::kRowsPerTile))) return rc;
-            if ((rc = tc::make_act_map(&m.f_y_store, ctx->bufY, C, rows, batch, 64, gcn::kRowsPerTile))) return rc;
+            if ((rc = tf::make_bvtc_map(&m.f_y_store, ctx->bufY, C, T, batch, true, 64, gcn::kFramesPerTile))) return rc;
             if ((rc = tc::make_f32_map(&m.f_gt, ctx->gT, cin, (long long)batch * T, 64, 8))) return rc;
             if ((rc = tc::make_f32_map(&m.f_gv, ctx->gV, cin, (long long)batch * V17, 64, V17))) return rc;
         }
@@ -356,64 +244,26 @@ int build_maps(Ctx *ctx, int T) {
     return GS_OK;
 }
 
-void base_program(tc::Program &p, int B, int T, int N, int kc, int relu, int tile_rows = tc::kTileM) {
-    memset(&p, 0, sizeof(p));
-    p.kc = kc;
-    p.N = N;
-    p.T = T;
-    p.rows_per_clip = T * V17;
-    p.tile_rows = tile_rows;
-    p.mtiles = cdiv(p.rows_per_clip, tile_rows);
-    p.ntiles = B * p.mtiles;
-    p.relu = relu;
-    p.a_bytes = tc::kTileM * kc * 2;
-}
-
-// Out = relu(In[rows,K] . W^T + bias): K in 64-wide chunks
-int dense_gemm(Ctx *ctx, int kid, const CUtensorMap &in, const CUtensorMap &w, const CUtensorMap &out,
-               const float *bias, int B, int T, int K, int N, cudaStream_t st, unsigned long long *trace = nullptr,
-               bool out_joint_major = false) {
-    tc::Launch L{};
-    base_program(L.prog, B, T, N, 64, 1, out_joint_major ? gcn::kRowsPerTile : tc::kTileM);
-    L.prog.trace = trace;
-    L.prog.out_joint_major = out_joint_major ? 1 : 0;
-    static const bool gemm_rev = getenv("GOLFER_GEMM_FWD") == nullptr;
-    L.prog.rev = gemm_rev ? 1 : 0;
-    L.prog.nchunks = K / 64;
-    L.prog.b_bytes[0] = N * 64 * 2;
-    for (int k = 0; k < L.prog.nchunks; ++k) {
-        tc::Chunk &c = L.prog.ch[k];
-        c.a_k = c.b_k = 64 * k;
-        c.n_size = N;
-        c.accum = k > 0;
-    }
-    L.mapA0 = L.mapA1 = in;
-    L.mapB0 = L.mapB1 = w;
-    L.mapOut = L.mapRes = out;
-    L.bias = bias;
-    const double rows = (double)B * T * V17;
-    L.flops = 2.0 * rows * K * N;
-    L.bytes = 2.0 * rows * (K + N);
-    return tc::launch(ctx, kid, L, st);
-}
-
 }  // namespace
 
 int bf16_path_create(Ctx *ctx) {
     const gs_config &c = ctx->cfg;
     const int R = c.num_branches;
     if (ctx->blocks.empty() || !ctx->blocks[0].has_res || c.in_channels != 3 ||
-        256 % (ctx->blocks[0].c / 4) != 0) {
-        set_error("bf16 path expects 3 input channels and block 0 to change width (residual projection)");
+        (ctx->blocks[0].c != 64 && ctx->blocks[0].c != 128)) {
+        set_error("bf16 path expects 3 input channels and a first block of width 64 or 128");
         return GS_ERR_UNSUPPORTED;
     }
+    int dmax = 1;
+    for (int r = 0; r < R; ++r) dmax = dmax > c.dilations[r] ? dmax : c.dilations[r];
     for (size_t i = 0; i < ctx->blocks.size(); ++i) {
         const BlockParams &b = ctx->blocks[i];
         const bool ok = (b.c % 64 == 0) && b.c <= 256 && (b.cr == 8 || b.cr == 16 || b.cr == 32 || b.cr == 64) &&
-                        (i == 0 || b.cin % 64 == 0);
+                        (i == 0 || b.cin % 64 == 0) && b.c == 4 * b.cj && dmax <= 16;
         if (!ok) {
-            set_error("bf16 tensor-core path needs widths in {64,128,256} and C/R in {8,16,32,64} "
-                      "(block %zu: cin=%d c=%d c/R=%d); use precision fp32 for this config", i, b.cin, b.c, b.cr);
+            set_error("bf16 tensor-core path needs widths in {64,128,256}, C/R in {8,16,32,64}, ST-joint reduction 4 "
+                      "and dilations <= 16 (block %zu: cin=%d c=%d c/R=%d); use precision fp32 for this config", i, b.cin,
+                      b.c, b.cr);
             return GS_ERR_UNSUPPORTED;
         }
     }
@@ -423,8 +273,7 @@ int bf16_path_create(Ctx *ctx) {
     }
     Bf16Path *bp = new Bf16Path();
     ctx->bf16 = bp;
-    if (const char *e = getenv("GOLFER_GCN_UNFUSED")) bp->fused_gcn = !(e[0] == '1');
-    if (const char *e = getenv("GOLFER_STJ_FFMA")) bp->stj_tc = !(e[0] == '1');
+    // instrumentation only (no alternative code paths hang off the environment)
     if (const char *e = getenv("GOLFER_DEBUG_XA")) bp->debug_xa = (e[0] == '1');
     if (const char *e = getenv("GOLFER_TRACE_GCN")) {
         if (e[0] == '1') {
@@ -433,11 +282,11 @@ int bf16_path_create(Ctx *ctx) {
             GS_CUDA(cudaMemset(bp->trace, 0, n * 8));
         }
     }
-    if (const char *e = getenv("GOLFER_TRACE_TC")) {
+    if (const char *e = getenv("GOLFER_TRACE_TCN")) {
         if (e[0] == '1') {
-            const size_t n = (size_t)GS_MAX_BLOCKS * 2 * 5 * tc::kTraceTiles * tc::kTraceEv;
-            GS_CUDA(cudaMalloc((void **)&bp->trace_tc, n * 8));
-            GS_CUDA(cudaMemset(bp->trace_tc, 0, n * 8));
+            const size_t n = (size_t)GS_MAX_BLOCKS * 4 * tf::kTrSteps * tf::kTrEv;
+            GS_CUDA(cudaMalloc((void **)&bp->trace_tcn, n * 8));
+            GS_CUDA(cudaMemset(bp->trace_tcn, 0, n * 8));
         }
     }
     const size_t nb = ctx->blocks.size();
@@ -492,7 +341,7 @@ int bf16_path_create(Ctx *ctx) {
             const float *brh = host(b.br);
             for (int n = 0; n < C; ++n) bias[n] += brh[n];
         }
-        if (bp->stj_tc && C == 4 * b.cj && (C == 64 || C == 128 || C == 256)) {
+        {   // ST-joint matrices in mma.sync fragment order
             const int Q = C / 64;
             const float *srcs[3] = {host(b.jW), host(b.jWt), host(b.jWv)};
             for (int w = 0; w < 3; ++w) {
@@ -506,9 +355,7 @@ int bf16_path_create(Ctx *ctx) {
         }
         GS_CUDA(cudaMalloc((void **)&bp->bias_t[i], C * sizeof(float)));
         GS_CUDA(cudaMemcpy(bp->bias_t[i], bias.data(), C * sizeof(float), cudaMemcpyHostToDevice));
-        // block 0 on tensor cores (front_mma_kernel): 3 input channels, a residual projection, C = 64 or 128;
-        // GOLFER_FRONT_FFMA=1 keeps the CUDA-core kernel
-        if (i == 0 && cin == 3 && b.has_res && (C == 64 || C == 128) && !getenv("GOLFER_FRONT_FFMA")) {
+        if (i == 0) {   // block 0 on warp-level tensor cores (front_mma_kernel)
             std::vector<float> bm;
             pack_front_matrix(host(b.Wg), host(b.bg), host(b.Wr), host(b.br), C, bm);
             GS_CUDA(cudaMalloc((void **)&bp->frontB, bm.size() * sizeof(float)));
@@ -532,20 +379,31 @@ void bf16_path_destroy(Ctx *ctx) {
             if (p) cudaFree(p);
     if (bp->frontB) cudaFree(bp->frontB);
     if (bp->trace) cudaFree(bp->trace);
-    if (bp->trace_tc) cudaFree(bp->trace_tc);
+    if (bp->trace_tcn) cudaFree(bp->trace_tcn);
     delete bp;
     ctx->bf16 = nullptr;
 }
 
+// Debug / parity hooks (tests/test_gpu_kernels.py, tools/trace_gcn.py): raw copies of the workspace tensors
+// of the LAST block that ran.  "X" gated block input [B,T,V,Cin]; "XA" aggregated input (GOLFER_DEBUG_XA=1);
+// "Y" GCN output, joint-major [B,V,T,C]; "U0"/"U1" block outputs before their gates [B,T,V,C] (ping-pong);
+// "R" block 0's projected input; "gT" [B,T,C] / "gV" [B,V,C] fp32 gates; "PT" / "PV" pooling sums; "seS" SE gate.
 int bf16_debug_read(Ctx *ctx, const char *name, void *host, size_t nbytes) {
     Bf16Path *bp = ctx->bf16;
     const void *src = nullptr;
     if (bp && !strcmp(name, "gcn_trace")) src = bp->trace;
-    else if (bp && !strcmp(name, "tc_trace")) src = bp->trace_tc;
+    else if (bp && !strcmp(name, "tcn_trace")) src = bp->trace_tcn;
     else if (!strcmp(name, "XA")) src = ctx->bufXA;
     else if (!strcmp(name, "X")) src = ctx->bufX;
     else if (!strcmp(name, "Y")) src = ctx->bufY;
-    else if (!strcmp(name, "H")) src = ctx->bufH;
+    else if (!strcmp(name, "R")) src = ctx->bufR;
+    else if (!strcmp(name, "U0")) src = ctx->bufU[0];
+    else if (!strcmp(name, "U1")) src = ctx->bufU[1];
+    else if (!strcmp(name, "gT")) src = ctx->gT;
+    else if (!strcmp(name, "gV")) src = ctx->gV;
+    else if (!strcmp(name, "PT")) src = ctx->PT;
+    else if (!strcmp(name, "PV")) src = ctx->PV;
+    else if (!strcmp(name, "seS")) src = ctx->seS;
     if (!src) {
         set_error("debug buffer '%s' not available", name);
         return GS_ERR_INVALID;
@@ -565,7 +423,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
     const double rows = (double)nframes * V17;
     const int nb = ctx->cfg.num_blocks, R = ctx->cfg.num_branches;
     const int last = upto_block >= 0 ? upto_block : nb - 1;
-    bf *X = (bf *)ctx->bufX, *XA = (bf *)ctx->bufXA, *Y = (bf *)ctx->bufY, *R0 = (bf *)ctx->bufR;
+    bf *XA = (bf *)ctx->bufXA, *Y = (bf *)ctx->bufY, *R0 = (bf *)ctx->bufR;
     const bf *Uprev = nullptr;
     for (int i = 0; i <= last; ++i) {
         ctx->cur_block = i;
@@ -573,27 +431,17 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         const BlockMaps &m = bp->maps[i];
         const int C = b.c, cin = b.cin, cr = b.cr;
         bf *U = (bf *)ctx->bufU[i & 1];
-        if (i == 0 && bp->frontB) {
+        const bool proj = (i > 0 && b.has_res);
+        if (i == 0) {
             const size_t smem = ((size_t)3 * V17 * V17 + 1 + (size_t)kFrontFrames * V17 * (cin + kFrontLd)) * sizeof(float);
             {
                 LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
                                rows * (cin * 4 + 4.0 * C));
                 front_mma_kernel<3><<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
-                    skel, ctx->in_scale, ctx->in_shift, b.A, bp->frontB, C, nframes, Y, R0);
+                    skel, ctx->in_scale, ctx->in_shift, b.A, bp->frontB, C, T, nframes, Y, R0);
             }
             GS_KERNEL_CHECK();
-        } else if (i == 0) {
-            const size_t smem = (size_t)front_smem(cin, C).total * sizeof(float);
-            if (smem > 48 * 1024)
-                GS_CUDA(cudaFuncSetAttribute(front_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            {
-                LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
-                               rows * (cin * 4 + 4.0 * C));
-                front_kernel<3><<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
-                    skel, ctx->in_scale, ctx->in_shift, b.A, b.Wg, b.bg, b.Wr, b.br, C, nframes, Y, R0);
-            }
-            GS_KERNEL_CHECK();
-        } else if (bp->fused_gcn) {
+        } else {
             gcn::LaunchGcn L{};
             L.mapX = m.f_x_load;
             L.mapXg = m.f_xg_store;
@@ -611,64 +459,46 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.ntiles = B * q.mtiles;
             q.gT = ctx->gT;
             q.gV = ctx->gV;
-            static const bool gcn_rev = getenv("GOLFER_GCN_REV") != nullptr;
-            q.rev = gcn_rev ? 1 : 0;
+            q.store_xg = 1;
             q.A = b.A;
             q.bias = b.bg;
             q.dbg_xa = (bp->debug_xa && cin * 128 <= 119 * 256) ? XA : nullptr;
             q.trace = bp->trace ? bp->trace + (size_t)i * 5 * gcn::kTraceTiles * gcn::kTraceEv : nullptr;
             L.flops = 2.0 * rows * (V17 * 3.0 * cin + 3.0 * cin * C);
-            L.bytes = 2.0 * rows * (2.0 * cin + C);
+            L.bytes = 2.0 * rows * ((q.store_xg ? 2.0 : 1.0) * cin + C);
             if ((rc = gcn::launch(ctx, K_B_GEMM_GCN, L, st))) return rc;
-        } else {
-            const size_t items = nframes * cin;
-            size_t g = (items + 255) / 256;
-            if (g > (size_t)ctx->sm_count * 32) g = (size_t)ctx->sm_count * 32;
-            {
-                LaunchScope ls(ctx, K_B_AGG, st, 2.0 * rows * V17 * 3 * cin, 2.0 * rows * cin * 5);
-                aggregate_kernel<bf, bf, 3><<<(int)g, 256, 0, st>>>(Uprev, ctx->gT, ctx->gV, nullptr, nullptr, b.A, T,
-                                                                   cin, nframes, X, XA);
-            }
-            GS_KERNEL_CHECK();
-            if ((rc = dense_gemm(ctx, K_B_GEMM_GCN, m.xa_in, m.wg, m.y_out, b.bg, B, T, 3 * cin, C, st))) return rc;
         }
-        const size_t trn = (size_t)5 * tc::kTraceTiles * tc::kTraceEv;
-        unsigned long long *tr = bp->trace_tc ? bp->trace_tc + (size_t)i * 2 * trn : nullptr;
-        if ((rc = dense_gemm(ctx, K_B_GEMM_TCN1, m.y_in, m.w1, m.h_out_jm, b.b1, B, T, C, C, st, tr, true))) return rc;
-        {   // dilated taps (+ residual projection) + residual + ReLU + pooling sums (tconv_window.cuh)
-            tw::LaunchTw L{};
-            L.maps = m.tw;
-            tw::Params &q = L.prm;
+        {   // branch 1x1 + dilated taps (+ residual projection) + residual + ReLU + pooling sums (tcn_fused.cuh)
+            tf::LaunchTf L{};
+            L.maps = m.tf;
+            tf::Params &q = L.prm;
             memset(&q, 0, sizeof(q));
-            const bool proj = (i > 0 && b.has_res);
             q.B = B; q.T = T; q.C = C; q.cr = cr; q.cin = cin;
             q.nbr = 64 / cr;
             q.proj = proj ? 1 : 0;
             q.nkx = proj ? cin / 64 : 0;
+            q.nky = C / 64;
             q.dmax = 1;
             for (int r = 0; r < R; ++r) {
                 q.dil[r] = ctx->cfg.dilations[r];
                 q.dmax = q.dmax > q.dil[r] ? q.dmax : q.dil[r];
             }
-            q.wrows = tw::kFramesTile + 2 * q.dmax;
-            q.ttiles = cdiv(T, tw::kFramesTile);
+            q.nout = tf::kWin - 2 * q.dmax;
+            q.ttiles = cdiv(T, q.nout);
             q.nboxes = C / 64;
             q.nq_items = B * q.ttiles;
-            // traversal order: the branch 1x1 GEMM walks its tiles from the last clip down (it then finds the tail
-            // of the GCN's Y still in L2: 2-4 % on that launch), so the tail of ITS output H is the first clips and
-            // this kernel walks forward (GOLFER_GEMM_FWD=1 / GOLFER_TCONV_REV=1 flip either: measured within 1 %)
-            static const bool tw_rev = getenv("GOLFER_TCONV_REV") != nullptr;
-            q.rev = tw_rev ? 1 : 0;
+            q.bias1 = b.b1;
             q.bias = bp->bias_t[i];
             q.PT = ctx->PT;
             q.PVpart = ctx->PVpart;
-            q.trace = tr ? tr + trn : nullptr;
-            L.flops = 2.0 * rows * (3.0 * cr * C + (proj ? (double)cin * C : 0.0));
+            q.trace = bp->trace_tcn ? bp->trace_tcn + (size_t)i * 4 * tf::kTrSteps * tf::kTrEv : nullptr;
+            L.flops = 2.0 * rows * ((double)C * C + 3.0 * cr * C + (proj ? (double)cin * C : 0.0));
             L.bytes = 2.0 * rows * (2.0 * C + (proj ? cin : C));
-            if ((rc = tw::launch(ctx, K_B_TCONV, L, st))) return rc;
+            if ((rc = tf::launch(ctx, K_B_TCONV, L, st))) return rc;
         }
         const float *stjp[3] = {bp->stjP[0][i], bp->stjP[1][i], bp->stjP[2][i]};
-        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, tw::kFramesTile, stjp[0] ? stjp : nullptr))) return rc;
+        const int dmax_all = [&] { int d = 1; for (int r = 0; r < R; ++r) d = d > ctx->cfg.dilations[r] ? d : ctx->cfg.dilations[r]; return d; }();
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, 4 * cdiv(T, tf::kWin - 2 * dmax_all), stjp))) return rc;
         Uprev = U;
     }
     ctx->cur_block = GS_MAX_BLOCKS;

@@ -778,16 +778,16 @@ features_kernel(const TU *__restrict__ U, const float *__restrict__ gT, const fl
 }
 
 // Host-side launcher for the attention tail of one block (stats -> SE -> ST-joint).
-// `stj_packed` (bf16 path): fragment-ordered TF32 copies of {W, Wt, Wv} for stj_tc_kernel.
-// `fused_chunk` > 0: PT / PVpart were already written by the producing kernel's epilogue with
-// chunks of that many frames (tc_gemm.cuh); 0: run stats_kernel here.
+// `stj_packed` (bf16 path): fragment-ordered fp16 copies of {W, Wt, Wv} for stj_tc_kernel.
+// `fused_nchunk` > 0: PT and that many PVpart partials per clip were already written by the producing
+// kernel's epilogue (tcn_fused.cuh); 0: run stats_kernel here.
 template <typename TU>
 int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T, cudaStream_t st,
-                     int fused_chunk = 0, const float *const *stj_packed = nullptr) {
+                     int fused_nchunk = 0, const float *const *stj_packed = nullptr) {
     constexpr int V = 17;
     const int C = bp.c;
-    const int nchunk = cdiv(T, fused_chunk > 0 ? fused_chunk : kStatChunk);
-    if (fused_chunk == 0) {
+    const int nchunk = fused_nchunk > 0 ? fused_nchunk : cdiv(T, kStatChunk);
+    if (fused_nchunk == 0) {
         dim3 grid(nchunk, B, cdiv(C, 128));
         {
             LaunchScope ls(ctx, K_STATS, st, 2.0 * B * T * V * C, (double)B * T * V * C * sizeof(TU));
