@@ -17,6 +17,8 @@ SOURCES = ["api.cu", "align.cu", "pose.cu", "segment_fp32.cu", "segment_bf16.cu"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    # instrumentation builds only (e.g. GOLFER_NVCC_EXTRA=-DGOLFER_TCN_TRACE with --force; tools/trace_tcn.py)
+    *os.environ.get("GOLFER_NVCC_EXTRA", "").split(),
 ]
 
 

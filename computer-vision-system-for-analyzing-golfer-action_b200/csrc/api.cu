@@ -191,8 +191,7 @@ int alloc_workspace(Ctx *ctx) {
     if ((rc = bytes(&ctx->bufU[0], rows * cmax * esz))) return rc;
     if ((rc = bytes(&ctx->bufU[1], rows * cmax * esz))) return rc;
     // pooling partials: 30-frame chunks (stats_kernel; the bf16 path pools per >= 96-frame tile of tcn_fused.cuh)
-    // fp32 path: 30-frame chunks; bf16 path: 4 partials (32-row quarters) per frame tile of >= 96 frames
-    const int nchunk = std::max((ctx->max_T + 29) / 30, 4 * ((ctx->max_T + 95) / 96));
+    const int nchunk = (ctx->max_T + 29) / 30;
     if ((rc = dmalloc(ctx, &ctx->PT, frames * cmax))) return rc;
     if ((rc = dmalloc(ctx, &ctx->PV, (size_t)ctx->max_B * c.num_joints * cmax))) return rc;
     if ((rc = dmalloc(ctx, &ctx->PVpart, (size_t)ctx->max_B * nchunk * c.num_joints * cmax))) return rc;

@@ -498,7 +498,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         }
         const float *stjp[3] = {bp->stjP[0][i], bp->stjP[1][i], bp->stjP[2][i]};
         const int dmax_all = [&] { int d = 1; for (int r = 0; r < R; ++r) d = d > ctx->cfg.dilations[r] ? d : ctx->cfg.dilations[r]; return d; }();
-        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, 4 * cdiv(T, tf::kWin - 2 * dmax_all), stjp))) return rc;
+        if ((rc = launch_attention<bf>(ctx, b, U, B, T, st, cdiv(T, tf::kWin - 2 * dmax_all), stjp))) return rc;
         Uprev = U;
     }
     ctx->cur_block = GS_MAX_BLOCKS;

@@ -26,9 +26,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait suspend-time hint (as CUTLASS's ClusterBarrier::wait): without it a try_wait on an incomplete phase
-// returns after ~50 cycles and the waiting warps' retry loops took ~20 % of the SM's issue slots (ncu, round 2).
-constexpr uint32_t kMbarSuspendHint = 0x989680u;
 // Wait for the phase with the given parity.  The retry loop lives INSIDE one asm statement (as in
 // CUTLASS's ClusterBarrier::wait): a C++ loop on the per-thread try_wait predicate makes the compiler
 // treat everything after it as potentially divergent, which pushes the MMA / TMA operands into vector
@@ -39,12 +36,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(kMbarSuspendHint)
+        "r"(parity)
         : "memory");
 }
 // The same on a precomputed 32-bit shared address (hot loops: no generic -> shared conversion per call)
@@ -53,12 +50,12 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity), "r"(kMbarSuspendHint)
+        "r"(parity)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
