@@ -184,7 +184,14 @@ int alloc_workspace(Ctx *ctx) {
     int rc;
     auto bytes = [&](void **p, size_t n) { return dmalloc(ctx, (unsigned char **)p, n); };
     if ((rc = bytes(&ctx->bufX, rows * cmax * esz))) return rc;
-    if ((rc = bytes(&ctx->bufXA, rows * cmax * 3 * esz))) return rc;
+    // aggregated input: a real tensor on the fp32 path only; the bf16 path never stores it (gcn_fused.cuh) except as a
+    // debug dump of whole 128-row tiles when GOLFER_DEBUG_XA=1 (tests/test_gpu_kernels.py)
+    size_t xa_bytes = rows * cmax * 3 * esz;
+    if (c.precision == GS_PREC_BF16) {
+        const char *e = getenv("GOLFER_DEBUG_XA");
+        xa_bytes = (e && e[0] == '1') ? (size_t)ctx->max_B * ((ctx->max_T + 6) / 7) * 128 * 3 * cmax * 2 : 0;
+    }
+    if ((rc = bytes(&ctx->bufXA, xa_bytes))) return rc;
     if ((rc = bytes(&ctx->bufY, rows * cmax * esz))) return rc;
     if ((rc = bytes(&ctx->bufH, rows * cmax * esz))) return rc;
     if ((rc = bytes(&ctx->bufR, rows * cmax * esz))) return rc;

@@ -462,7 +462,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.store_xg = 1;
             q.A = b.A;
             q.bias = b.bg;
-            q.dbg_xa = (bp->debug_xa && cin * 128 <= 119 * 256) ? XA : nullptr;
+            q.dbg_xa = bp->debug_xa ? XA : nullptr;      // sized for whole tiles in alloc_workspace when the switch is on
             q.trace = bp->trace ? bp->trace + (size_t)i * 5 * gcn::kTraceTiles * gcn::kTraceEv : nullptr;
             L.flops = 2.0 * rows * (V17 * 3.0 * cin + 3.0 * cin * C);
             L.bytes = 2.0 * rows * ((q.store_xg ? 2.0 : 1.0) * cin + C);

@@ -214,3 +214,23 @@ def synth_skeletons(B: int, T: int, cfg: GolfSegConfig, seed: int = 0) -> np.nda
     if cfg.in_channels != 3:
         out = np.resize(out, (B, T, V, cfg.in_channels))
     return np.ascontiguousarray(out, dtype=np.float32)
+
+
+@torch.no_grad()
+def spread_head_params(cfg: GolfSegConfig, params: Dict[str, np.ndarray], calib_seed: int = 99, gain: float = 6.0):
+    """`v0-spread`: a copy of `params` whose head is re-centred and re-scaled so that per-frame labels spread
+    over the classes with O(1) margins (option (a)).  With the plain random-init head 95 %
+    of the frames of a synthetic clip fall into one class, so label parity would exercise almost no decision
+    boundary.  Only head.W / head.b change (the network body, hence every kernel's work, is v0's); the
+    calibration runs the oracle on 4 seeded clips: per class k the logit is standardised over those frames
+    (z_k = (l_k - mean_k) / std_k) and multiplied by `gain`, expressed as new head weights:
+        W'[:, k] = W[:, k] * gain / std_k,   b'[k] = (b[k] - mean_k) * gain / std_k."""
+    net = SegNet(cfg, params)
+    x = torch.from_numpy(synth_skeletons(4, 96, cfg, seed=calib_seed))
+    logits = net(x).reshape(-1, cfg.num_classes)
+    mean, std = logits.mean(0).numpy(), logits.std(0).numpy()
+    out = dict(params)
+    scale = (gain / std).astype(np.float32)
+    out["head.W"] = (params["head.W"] * scale[None, :]).astype(np.float32)
+    out["head.b"] = ((params["head.b"] - mean) * scale).astype(np.float32)
+    return out

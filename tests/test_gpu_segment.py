@@ -24,17 +24,28 @@ def _rel(got, want):
     return float(np.abs(got - want).max() / np.abs(want).max())
 
 
-def _label_check(logits_want, labels_got, tol):
+def label_parity(logits_want, labels_got, tol):
+    """Counts behind the label policy: frames, frames whose oracle top-2 margin exceeds 4 x tol x max|logit|,
+    label mismatches over all frames and over the frames above the margin, classes the oracle uses."""
     want = osegnet.labels_from_logits(logits_want)
     top2 = np.sort(logits_want, axis=-1)[..., -2:]
     margin = top2[..., 1] - top2[..., 0]
     safe = margin > 4 * tol * np.abs(logits_want).max()
-    mism_safe = int(np.count_nonzero(want[safe] != labels_got[safe]))
-    mism_all = int(np.count_nonzero(want != labels_got))
-    print(f"labels: {want.size} frames, {int(safe.sum())} above margin, mismatches {mism_all} "
-          f"(above margin {mism_safe})")
-    assert mism_safe == 0
-    return mism_all
+    return {"frames": int(want.size), "above_margin": int(safe.sum()),
+            "mismatches_all": int(np.count_nonzero(want != labels_got)),
+            "mismatches_above_margin": int(np.count_nonzero(want[safe] != labels_got[safe])),
+            "classes_used": int(np.count_nonzero(np.bincount(want.ravel(), minlength=logits_want.shape[-1])))}
+
+
+def _label_check(logits_want, labels_got, tol, exact=False):
+    """Asserts the policy and RETURNS the counts (recorded by the callers that pin a config).  exact=True
+    (fp32 path): no mismatch on any frame."""
+    c = label_parity(logits_want, labels_got, tol)
+    print(f"labels: {c}")
+    assert c["mismatches_above_margin"] == 0
+    if exact:
+        assert c["mismatches_all"] == 0
+    return c
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -48,7 +59,7 @@ def test_golden_fixtures(golden_dir, prec):
         seg = golfer_b200.Segmenter(cfg, params, precision=prec, max_B=skel.shape[0], max_T=skel.shape[1])
         logits, labels = seg.segment(torch.from_numpy(skel).cuda(), return_labels=True)
         assert _rel(logits.cpu().numpy(), g[f"{tag}_logits"]) < TOL[prec]
-        _label_check(g[f"{tag}_logits"], labels.cpu().numpy(), TOL[prec])
+        _label_check(g[f"{tag}_logits"], labels.cpu().numpy(), TOL[prec], exact=(prec == "fp32"))
         seg.ctx.close()
 
 
@@ -64,7 +75,72 @@ def test_matches_oracle(prec, B, T):
     err = _rel(logits.cpu().numpy(), want)
     print(f"{prec} B={B} T={T}: rel err {err:.3e}")
     assert err < TOL[prec]
-    _label_check(want, labels.cpu().numpy(), TOL[prec])
+    _label_check(want, labels.cpu().numpy(), TOL[prec], exact=(prec == "fp32"))
+    seg.ctx.close()
+
+
+def _record(name, payload):
+    """Label-parity / error figures of the pinned configs, kept next to the test logs (gpurun_out/ travels back)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "label_parity_tests.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = payload
+    json.dump(data, open(path, "w"), indent=1)
+
+
+@pytest.mark.parametrize("prec,nsample", [("bf16", 32), ("fp32", 8)])
+def test_headline_config_batch256_t300(prec, nsample):
+    """BASELINE.json configs[1] itself: 256 clips x 300 frames through the persistent kernels' full tile walks
+    (reverse orders, multi-tile pipelines, TMEM double-buffer phases), a strided sample of clips against the
+    oracle, and clip i of the big batch bit-identical to the same clip run alone."""
+    cfg = golfer_b200.V0
+    params = golfer_b200.params.make_params(cfg, 1234)
+    B, T = 256, 300
+    skel = osegnet.synth_skeletons(B, T, cfg, seed=0)
+    seg = golfer_b200.Segmenter(cfg, params, precision=prec, max_B=B, max_T=T)
+    x = torch.from_numpy(skel).cuda()
+    logits, labels = seg.segment(x, return_labels=True)
+    logits, labels = logits.clone(), labels.clone()
+    idx = np.unique(np.concatenate([np.arange(0, B, B // nsample), [B - 1]]))
+    want = osegnet.segment_ref(cfg, params, skel[idx])
+    got = logits[idx].cpu().numpy()
+    err = _rel(got, want)
+    print(f"{prec} B=256 T=300: rel err {err:.3e} over {len(idx)} sampled clips")
+    assert err < TOL[prec]
+    counts = _label_check(want, labels[idx].cpu().numpy(), TOL[prec], exact=(prec == "fp32"))
+    assert torch.equal(labels, logits.argmax(-1).to(torch.uint8))        # the kernel's arg-max of its own logits
+    for i in (0, 37, 255):
+        one = seg.segment(x[i:i + 1])
+        assert torch.equal(one[0], logits[i]), i                          # batch-independent, tile-walk-independent
+    _record(f"v0_{prec}_B256_T300", {"rel_err": err, "clips_checked": int(len(idx)), **counts})
+    seg.ctx.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_spread_head_labels(prec):
+    """`v0-spread` (oracle/segnet.py:spread_head_params): same body, head re-centred so the labels use all 9
+    classes with O(1) margins - label parity where decision boundaries are actually exercised.  fp32: every
+    frame identical.  bf16: the standardised head amplifies the bf16 logit error relative to the margins, so
+    mismatches are COUNTED and bounded (regression guard), and none is allowed above the policy margin."""
+    cfg = golfer_b200.V0
+    params = osegnet.spread_head_params(cfg, golfer_b200.params.make_params(cfg, 1234))
+    B, T = 8, 300
+    skel = osegnet.synth_skeletons(B, T, cfg, seed=5)
+    want = osegnet.segment_ref(cfg, params, skel)
+    seg = golfer_b200.Segmenter(cfg, params, precision=prec, max_B=B, max_T=T)
+    logits, labels = seg.segment(torch.from_numpy(skel).cuda(), return_labels=True)
+    c = label_parity(want, labels.cpu().numpy(), TOL[prec])
+    err = _rel(logits.cpu().numpy(), want)
+    print(f"spread head {prec}: rel err {err:.3e} labels {c}")
+    assert c["classes_used"] >= 6
+    if prec == "fp32":
+        assert c["mismatches_all"] == 0 and err < 1e-4
+    else:
+        assert c["mismatches_above_margin"] == 0
+        assert c["mismatches_all"] <= 0.05 * c["frames"]
+    _record(f"v0_spread_{prec}_B8_T300", {"rel_err": err, **c})
     seg.ctx.close()
 
 
@@ -147,4 +223,27 @@ def test_bad_shapes_raise():
         seg.segment(torch.zeros(2, 8, 16, 3, device="cuda"))
     with pytest.raises(golfer_b200.GolferError):
         seg.segment(torch.zeros(3, 8, 17, 3, device="cuda"))
+    seg.ctx.close()
+
+
+def test_bf16_property_sweep_small_shapes():
+    """Hypothesis sweep over (B <= 4, T <= 200): ragged last tiles of both tilings (7-frame GCN tiles, 120-frame
+    temporal tiles), T below the largest dilation, single-frame clips."""
+    from hypothesis import given, settings, strategies as st
+    cfg = golfer_b200.V0
+    params = golfer_b200.params.make_params(cfg, 1234)
+    net = osegnet.SegNet(cfg, params)
+    seg = golfer_b200.Segmenter(cfg, params, precision="bf16", max_B=4, max_T=200)
+
+    @settings(max_examples=12, deadline=None, derandomize=True)
+    @given(B=st.integers(1, 4), T=st.integers(1, 200), seed=st.integers(0, 1000))
+    def check(B, T, seed):
+        skel = osegnet.synth_skeletons(B, T, cfg, seed=seed)
+        with torch.no_grad():
+            want = net(torch.from_numpy(skel)).numpy()
+        got = seg.segment(torch.from_numpy(skel).cuda()).cpu().numpy()
+        assert got.shape == want.shape and np.isfinite(got).all()
+        assert _rel(got, want) < TOL["bf16"], (B, T, seed)
+
+    check()
     seg.ctx.close()

@@ -149,3 +149,19 @@ def test_golden_segnet(golden_dir):
 def test_label_rule_first_max():
     l = np.array([[[0.0, 1.0, 1.0], [2.0, 2.0, 1.0]]], np.float32)
     assert segnet.labels_from_logits(l).tolist() == [[1, 0]]
+
+
+def test_adjacency_matches_independent_hop_distance_oracle():
+    """the product's adjacency (params.build_adjacency, BFS + per-pair loop) against the
+    oracle's independent formulation (matrix-power hop distances + masks, its own edge list)."""
+    from oracle import adjacency
+    A_product = golfer_b200.params.build_adjacency(golfer_b200.V0)
+    A_oracle = adjacency.spatial_partitions()
+    assert A_product.dtype == A_oracle.dtype == np.float32
+    assert np.array_equal(A_product, A_oracle)
+    # the edge lists were written independently: same undirected edge set
+    mine = {tuple(sorted(e)) for limb in adjacency.EDGES_BY_LIMB.values() for e in limb}
+    theirs = {tuple(sorted(e)) for e in golfer_b200.config.COCO_EDGES}
+    assert mine == theirs and len(mine) == 16
+    hop = adjacency.hop_distance_matrix()
+    assert hop[0, 15] == 4 and hop[15, 16] == 8 and hop[3, 4] == 4     # ankle-nose, ankle-ankle, ear-ear
