@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_traffic.json")
 METRIC = "swing clips/sec (T=300,V=17)"
 UNIT = "clips/s"
 T_FRAMES = 300
@@ -53,6 +54,10 @@ def parse_args():
     ap.add_argument("--clips", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-align", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extras (pipeline / stress / next rows / probes)")
+    ap.add_argument("--gather", default="labels", choices=["labels", "logits"],
+                    help="what every step all-gathers for N > 1: u8 per-frame labels (default, 77 KB per GPU) or the fp32 "
+                         "logits (2.8 MB per GPU; measured separately in extras.gather_logits either way)")
     return ap.parse_args()
 
 
@@ -207,6 +212,33 @@ def synth_pairs(N, T, seed):
 _CPU_CACHE = {}
 
 
+def label_parity(logits_want, logits_got, labels_got, tol):
+    """The label policy's counts for one batch: the oracle's arg-max against the labels the
+    GPU produced; `above_margin` = frames whose oracle top-2 margin exceeds 4 x tol x max|logit|."""
+    want = np.argmax(logits_want, -1).astype(np.uint8)
+    top2 = np.sort(logits_want, axis=-1)[..., -2:]
+    safe = (top2[..., 1] - top2[..., 0]) > 4 * tol * np.abs(logits_want).max()
+    return {"frames": int(want.size), "above_margin": int(safe.sum()),
+            "mismatches_all": int(np.count_nonzero(want != labels_got)),
+            "mismatches_above_margin": int(np.count_nonzero(want[safe] != labels_got[safe])),
+            "classes_used": int(np.count_nonzero(np.bincount(want.ravel(), minlength=logits_want.shape[-1]))),
+            "logits_rel_err": float(np.abs(logits_got - logits_want).max() / np.abs(logits_want).max()),
+            "tolerance": tol}
+
+
+def cpu_oracle_logits(x, spread: bool = False):
+    """Oracle logits of clips `x` (checker use inside the cpu_baseline leg: label parity of the timed batch)."""
+    import golfer_b200
+    from oracle import segnet
+    cfg = golfer_b200.V0
+    params = golfer_b200.params.make_params(cfg, 1234)
+    if spread:
+        params = segnet.spread_head_params(cfg, params)
+    net = segnet.SegNet(cfg, params)
+    with torch.no_grad():
+        return np.concatenate([net(x[i:i + 2]).numpy() for i in range(0, x.shape[0], 2)]), params
+
+
 def cpu_segment_rate(n_clips: int, threads: int, repeats: int = 1):
     """Oracle (fp32 PyTorch, CPU) clips/s on a bounded sample of the same workload."""
     import golfer_b200
@@ -282,31 +314,27 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ pipeline ----
-def run_pipeline(args, golfer_b200, dist, dev, world, rank, local):
-    """BASELINE configs[3]: segment + align over `--clips` synthetic clips sharded over the GPUs (contiguous
-    shards, 256-clip batches), pairs = (clip 2i, clip 2i+1) cut to 300 frames, u8 labels and padded paths
-    gathered with NCCL after every batch.  One JSON line: whole-job clips/s and pairs/s."""
-    from golfer_b200.shard import shard_range
-    cfg = golfer_b200.V0
-    lo, hi = shard_range(args.clips, rank, world)
+def pipeline_measure(golfer_b200, seg, actx, dist, dev, world, rank, clips, warmup, precision):
+    """BASELINE configs[3]: segment + align over `clips` synthetic clips sharded over the GPUs (contiguous
+    shards, 256-clip batches), pairs = (clip 2i, clip 2i+1) cut to 300 frames, u8 labels and int16 padded paths
+    gathered (shard.gather_shards: NCCL all-gather) after every batch.  Strong scaling: total work fixed."""
+    from golfer_b200.shard import gather_shards, shard_range
+    lo, hi = shard_range(clips, rank, world)
     nb = BATCH
-    seg = golfer_b200.Segmenter(cfg, seed=1234, precision=args.precision, device=local, max_B=nb, max_T=T_FRAMES)
-    actx = golfer_b200.host.Context(local)
     skel = synth_skel(nb, T_FRAMES, seed=rank).to(dev)          # one resident synthetic batch, reused
-    maxL = 2 * T_FRAMES - 1
-    glab = torch.empty((world * nb, T_FRAMES), dtype=torch.uint8, device=dev) if dist is not None else None
-    gpath = torch.empty((world * (nb // 2), maxL, 2), dtype=torch.int32, device=dev) if dist is not None else None
+    xy = skel[..., :2].contiguous()
+    sa, sb = xy[0::2].contiguous(), xy[1::2].contiguous()
 
     def batch_step():
         logits, labels = seg.segment(skel, return_labels=True)
-        xy = skel[..., :2].contiguous()
-        cost, path, plen = golfer_b200.host.align_batch(xy[0::2], xy[1::2], ctx=actx)
+        cost, path, plen = golfer_b200.host.align_batch(sa, sb, ctx=actx)
         if dist is not None:
-            dist.all_gather_into_tensor(glab, labels)
-            dist.all_gather_into_tensor(gpath, path)
+            gather_shards(labels, world * nb, dist)
+            gather_shards(path.to(torch.int16), world * (nb // 2), dist)     # frame indices < 32768
+            gather_shards(plen, world * (nb // 2), dist)
         return logits
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         batch_step()
     torch.cuda.synchronize()
     if dist is not None:
@@ -323,16 +351,64 @@ def run_pipeline(args, golfer_b200, dist, dev, world, rank, local):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    return {"metric": "pipeline clips/sec (segment + align, T=300)", "value": clips / (ms * 1e-3), "unit": "clips/s",
+            "pairs_per_s": (clips // 2) / (ms * 1e-3), "n_gpus": world, "steps": nbatches, "warmup": max(warmup, 1),
+            "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "bf16" if precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: {clips} clips sharded over {world} GPU(s), 256-clip batches, "
+                                   "segment -> labels, align(clip 2i, clip 2i+1), NCCL all-gather of u8 labels and int16 "
+                                   "paths per batch"}}
+
+
+def run_pipeline(args, golfer_b200, dist, dev, world, rank, local):
+    seg = golfer_b200.Segmenter(golfer_b200.V0, seed=1234, precision=args.precision, device=local, max_B=BATCH,
+                                max_T=T_FRAMES)
+    actx = golfer_b200.host.Context(local)
+    line = pipeline_measure(golfer_b200, seg, actx, dist, dev, world, rank, args.clips, args.warmup, args.precision)
     if rank == 0:
-        print(json.dumps({
-            "metric": "pipeline clips/sec (segment + align, T=300)", "value": args.clips / (ms * 1e-3), "unit": "clips/s",
-            "pairs_per_s": (args.clips // 2) / (ms * 1e-3), "n_gpus": world, "steps": nbatches, "warmup": max(args.warmup, 1),
-            "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[3]: {args.clips} clips sharded over {world} GPU(s), 256-clip batches, "
-                                   "segment -> labels, align(clip 2i, clip 2i+1), NCCL all-gather of u8 labels and paths per batch"}}),
-            flush=True)
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def stress_measure(golfer_b200, dist, dev, world, rank, local, precision, steps, warmup):
+    """BASELINE configs[4]: 1800-frame clips, 8 temporal branches, batch 64 over the GPUs (strong scaling of a fixed
+    64-clip batch; u8 labels gathered in-step)."""
+    from golfer_b200.shard import gather_shards
+    cfg = golfer_b200.V0_STRESS
+    T, Bg = 1800, 64
+    B = max(Bg // world, 1)
+    seg = golfer_b200.Segmenter(cfg, seed=1234, precision=precision, device=local, max_B=B, max_T=T)
+    skel = synth_skel(B, T, seed=100 + rank).to(dev)
+
+    def step():
+        logits, labels = seg.segment(skel, return_labels=True)
+        if dist is not None:
+            gather_shards(labels, world * B, dist)
+
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    seg.ctx.close()
+    return {"metric": "stress clips/sec (T=1800, 8 branches)", "value": world * B * steps / (ms * 1e-3), "unit": "clips/s",
+            "ms_per_step": ms / steps, "clips_per_gpu": B, "global_batch": world * B, "n_gpus": world, "steps": steps,
+            "scaling": "strong", "flops_per_clip": cfg.flops_per_clip(T),
+            "tflops": cfg.flops_per_clip(T) * world * B * steps / (ms * 1e-3) / 1e12,
+            "config": {"workload": f"BASELINE configs[4]: GolfSegConfig {cfg.version}, {world * B} clips x 1800 frames over "
+                                   f"{world} GPU(s), u8 labels gathered in-step"}}
 
 
 # ------------------------------------------------------------------ GPU arm -----
@@ -376,6 +452,7 @@ def main():
         B = max(64 // world, 1) if args.batch == BATCH else args.batch
         args.no_align = True
         args.no_cpu_baseline = True
+        args.no_extras = True
 
     def barrier():
         torch.cuda.synchronize()
@@ -394,13 +471,13 @@ def main():
                                 max_T=T_FRAMES)
     skel_host = synth_skel(B, T_FRAMES, seed=rank).pin_memory()
     skel = skel_host.to(dev)
-    gathered = torch.empty((world * B, T_FRAMES, cfg.num_classes), device=dev) if dist is not None else None
+    from golfer_b200.shard import gather_shards
 
     def seg_step():
-        logits = seg.segment(skel)
-        if dist is not None:
-            dist.all_gather_into_tensor(gathered, logits)
-        return logits
+        logits, labels = seg.segment(skel, return_labels=True)
+        if dist is not None:      # the tested path (tests/test_sharding.py, tests/test_gpu_multi.py) is the timed path
+            gather_shards(logits if args.gather == "logits" else labels, world * B, dist)
+        return logits, labels
 
     # nvidia-smi needs ~0.2 s before its first sample: start it before the warm-up and keep
     # only samples taken under load (clocks.sm above half of max) for the median
@@ -416,7 +493,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        seg_step()
+        last_logits, last_labels = seg_step()
     e1.record()
     barrier()
     seg.ctx.profile(False)
@@ -463,10 +540,11 @@ def main():
                              "ms_per_launch_by_block": {str(bk): round(bv["ms"] / bv["launches"], 4)
                                                         for bk, bv in v.get("blocks", {}).items()}}
         top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        traffic = None      # ncu dram bytes per launch of that kernel (profiles/r1_traffic.json, same workload)
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath) and B == BATCH:
-            traffic = json.load(open(tpath)).get(top, {}).get("bytes_per_launch")
+        # ncu dram bytes per launch of that kernel: from the ncu --set full capture of THIS code state
+        # (profiles/r2_traffic.json, written by tools/ncu_summary.py --traffic from the capture of tools/ncu_run.sh)
+        traffic = None
+        if os.path.exists(TRAFFIC_JSON) and B == BATCH:
+            traffic = json.load(open(TRAFFIC_JSON)).get(top, {}).get("bytes_per_launch")
         tensor_bound = "gemm" in top or "tconv" in top
         if tensor_bound:
             ach = tv["flops"] / tv["ms"] / 1e9
@@ -501,12 +579,13 @@ def main():
         a, b = a_host.to(dev), b_host.to(dev)
         actx = golfer_b200.host.Context(local)
         maxL = 2 * T_FRAMES - 1
-        gpath = torch.empty((world * N, maxL, 2), dtype=torch.int32, device=dev) if dist is not None else None
 
         def al_step():
             cost, path, plen = golfer_b200.host.align_batch(a, b, ctx=actx)
-            if dist is not None:
-                dist.all_gather_into_tensor(gpath, path)
+            if dist is not None:       # int16 halves the only sizeable collective of the job (frame indices < 32768)
+                gather_shards(path.to(torch.int16), world * N, dist)
+                gather_shards(plen, world * N, dist)
+                gather_shards(cost, world * N, dist)
             return cost
 
         for _ in range(W):
@@ -552,9 +631,8 @@ def main():
                     "all_repetitions": [world * N * K / t for t in al_runs]},
             "roofline": {"kernel": "dtw_wavefront", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
                          "unit": "GB/s", "frac": ach / peaks["hbm"] if ach else None,
-                         "traffic": (json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-                                     .get("dtw_wavefront", {}).get("bytes_per_launch")
-                                     if os.path.exists(os.path.join(ROOT, "profiles", "r1_traffic.json")) else None),
+                         "traffic": (json.load(open(TRAFFIC_JSON)).get("dtw_wavefront", {}).get("bytes_per_launch")
+                                     if os.path.exists(TRAFFIC_JSON) else None),
                          "note": "compulsory bytes 86,396 B/pair: HBM is not the binding limit (SURVEY.md 7 item 4); "
                                  "see fp32_pipe"},
         }
@@ -611,16 +689,68 @@ def main():
                                  "note": "gs_align_phase, same 4096 pairs, 8 equal phases, penalty 0.5"}
         ectx.close()
 
+    if not args.no_extras and args.workload == "segment":
+        # ---- BASELINE configs[3] and configs[4] on every line, so the 1-8 GPU scaling run captures them (strong scaling)
+        pctx = golfer_b200.host.Context(local)
+        pclips = min(args.clips, 65536)
+        extras["pipeline"] = pipeline_measure(golfer_b200, seg, pctx, dist, dev, world, rank, pclips, 1, args.precision)
+        pctx.close()
+        extras["stress"] = stress_measure(golfer_b200, dist, dev, world, rank, local, args.precision, 5, 2)
+        if dist is not None:
+            # the collective alternatives of one segment step, each timed alone in-stream (20 repetitions)
+            def time_gather(t, n_total):
+                for _ in range(3):
+                    gather_shards(t, n_total, dist)
+                barrier()
+                e0.record()
+                for _ in range(20):
+                    gather_shards(t, n_total, dist)
+                e1.record()
+                barrier()
+                return max_over_ranks(e0.elapsed_time(e1)) / 20
+            extras["gather_ms"] = {"u8_labels": time_gather(last_labels, world * B),
+                                   "fp32_logits": time_gather(last_logits, world * B),
+                                   "bytes_per_gpu": {"u8_labels": int(last_labels.numel()),
+                                                     "fp32_logits": int(last_logits.numel() * 4)}}
+        if not args.no_align:
+            # what bounds the DTW e2e number at N > 1: the pinned-host -> device copies of all ranks share the host's
+            # memory system and PCIe root ports; every rank copies its 2 x 167 MB at the same time, 5 repetitions
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                a.copy_(a_host, non_blocking=True)
+                b.copy_(b_host, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            nbytes = 5.0 * (a_host.numel() + b_host.numel()) * 4
+            extras["h2d_probe"] = {"gbs_per_rank": nbytes / dt / 1e9, "gbs_all_ranks": world * nbytes / dt / 1e9,
+                                   "pairs_per_s_bound": world * 5 * N / dt,
+                                   "note": "concurrent pinned H2D of the align inputs on every rank: the ceiling of align.e2e"}
+
     clocks = sampler.stop() if rank == 0 else None   # covers every timed region above
 
     # ---- CPU oracle timed beside it (rank 0, N=1 only; bounded sample) ---------------
     cpu_baseline = None
+    label_par = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         rate, dt = cpu_segment_rate(128, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"128 clips of T={T_FRAMES} (half of the 256-clip batch) in {dt:.1f}s, "
                                   f"oracle/segnet.py fp32 on torch CPU, {cores} threads"}
+        # label parity of the timed batch itself (checker use of the oracle): 32 strided clips of the 256
+        idx = torch.arange(0, B, max(B // 32, 1))
+        want, _ = cpu_oracle_logits(skel_host[idx])
+        tol = 1e-2 if args.precision == "bf16" else 1e-5
+        label_par = {"v0": label_parity(want, last_logits[idx.to(dev)].cpu().numpy(), last_labels[idx.to(dev)].cpu().numpy(), tol)}
+        label_par["v0"]["clips_checked"] = int(idx.numel())
+        # and with the spread head (all 9 classes in use; oracle/segnet.py:spread_head_params): 8 clips
+        wants, sparams = cpu_oracle_logits(skel_host[:8], spread=True)
+        sseg = golfer_b200.Segmenter(cfg, sparams, precision=args.precision, device=local, max_B=8, max_T=T_FRAMES)
+        sl, sb = sseg.segment(skel[:8], return_labels=True)
+        label_par["v0_spread"] = label_parity(wants, sl.cpu().numpy(), sb.cpu().numpy(), tol)
+        label_par["v0_spread"]["clips_checked"] = 8
+        sseg.ctx.close()
         if align_obj is not None:
             ar, adt = cpu_align_rate(2048, cores)
             align_obj["cpu_baseline"] = {"value": ar, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -636,9 +766,11 @@ def main():
                                    f"(BASELINE configs[{4 if args.workload == 'stress' else 1}])",
                        "global_batch": world * B, "frames": T_FRAMES, "parallelism": f"dp{world}",
                        "l2_policy": "per-step working set (activations, several hundred MB) exceeds the 126 MB L2",
-                       "collective": "all_gather(logits) inside each step" if world > 1 else "none"},
+                       "collective": (f"all_gather({'fp32 logits' if args.gather == 'logits' else 'u8 labels'}) inside each step "
+                                      "(shard.gather_shards)") if world > 1 else "none"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "whole_net": whole_net, "kernels": kernels, "cpu_baseline": cpu_baseline, "align": align_obj,
+            "whole_net": whole_net, "kernels": kernels, "cpu_baseline": cpu_baseline, "label_parity": label_par,
+            "align": align_obj,
             "extras": extras or None,
         }
         print(json.dumps(line), flush=True)

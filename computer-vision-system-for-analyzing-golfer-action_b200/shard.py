@@ -35,6 +35,10 @@ def gather_shards(local, n_total: int, dist=None, group=None):
         import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return local
+    if local.dtype == torch.int16:
+        # the NCCL process group has no 16-bit integer type: an all-gather only moves bytes, so int16 payloads
+        # (alignment paths) travel as float16 bit patterns
+        return gather_shards(local.view(torch.float16), n_total, dist, group).view(torch.int16)
     world = dist.get_world_size(group)
     sizes = shard_sizes(n_total, world)
     if local.shape[0] != sizes[dist.get_rank(group)]:

@@ -65,6 +65,10 @@ def _worker(rank, world, port, n_clips, n_pairs, out_dir):
 
         logits = run_sharded(seg_fn, [skel])
         cost, path, plen = run_sharded(align_fn, [a, b])
+        # the int16 form the bench gathers (bit patterns travel as float16: NCCL has no 16-bit integer type)
+        _, path16, _ = run_sharded(lambda x, y: tuple(t.to(torch.int16) if t.dtype == torch.int32 and t.dim() == 3 else t
+                                                      for t in align_fn(x, y)), [a, b])
+        assert path16.dtype == torch.int16 and torch.equal(path16.to(torch.int32), path)
         if rank == 0:
             np.savez(os.path.join(out_dir, f"gathered_w{world}.npz"), logits=logits.numpy(), cost=cost.numpy(),
                      path=path.numpy(), plen=plen.numpy())
