@@ -688,6 +688,42 @@ def main():
         extras["align_phase"] = {"ms": ms, "pairs_per_s": N / (ms * 1e-3),
                                  "note": "gs_align_phase, same 4096 pairs, 8 equal phases, penalty 0.5"}
         ectx.close()
+        # no shape cliff: the pipelined sweep takes Ta < Tb by exchanging the sequences inside the launch
+        rect = {}
+        for Ta, Tb in ((300, 257), (257, 300)):
+            ra_, rb_ = a[:, :Ta].contiguous(), b[:, :Tb].contiguous()
+            for _ in range(W):
+                golfer_b200.host.align_batch(ra_, rb_, ctx=actx)
+            e0.record()
+            for _ in range(K):
+                golfer_b200.host.align_batch(ra_, rb_, ctx=actx)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / K
+            rect[f"{Ta}x{Tb}"] = {"ms": ms, "pairs_per_s": N / (ms * 1e-3), "cells_per_s": N * Ta * Tb / (ms * 1e-3)}
+        extras["align_rect"] = rect
+        # learned alignment embedding: encoder + tensor-core cost GEMM + DP over the cost matrix
+        emb = golfer_b200.EmbedAligner(golfer_b200.params.pack_embed_blob(golfer_b200.params.make_embed_params()),
+                                       device=local)
+        for _ in range(W):
+            emb.align(a, b)
+        emb.ctx.profile_reset()
+        emb.ctx.profile(True)
+        e0.record()
+        for _ in range(K):
+            emb.align(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        emb.ctx.profile(False)
+        ms = e0.elapsed_time(e1) / K
+        ep = emb.ctx.profile_read()
+        extras["align_embed"] = {"ms": ms, "pairs_per_s": N / (ms * 1e-3),
+                                 "kernels_ms": {k: v["ms"] / K for k, v in ep.items()},
+                                 "cost_gemm_tflops": (ep["embed_cost_gemm"]["flops"] / ep["embed_cost_gemm"]["ms"] / 1e9
+                                                      if "embed_cost_gemm" in ep else None),
+                                 "note": "gs_align_embed, same 4096 pairs of 300x300: MLP 34-128-128 per frame, "
+                                         "cost = Gram form on tcgen05 (K = 128), DP over the materialised cost matrix"}
+        emb.ctx.close()
 
     if not args.no_extras and args.workload == "segment":
         # ---- BASELINE configs[3] and configs[4] on every line, so the 1-8 GPU scaling run captures them (strong scaling)

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "libgolfer_b200.so")
-SOURCES = ["api.cu", "align.cu", "pose.cu", "segment_fp32.cu", "segment_bf16.cu"]
+SOURCES = ["api.cu", "align.cu", "align_embed.cu", "pose.cu", "segment_fp32.cu", "segment_bf16.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -48,7 +48,8 @@ const char *kernel_name(int id) {
     static const char *names[K_COUNT] = {
         "aggregate_fp32", "gemm_gcn_fp32", "gemm_tcn1x1_fp32", "gemm_res_fp32", "tconv_fp32", "stats", "se_gate",
         "stj_gate", "head", "features", "dtw_wavefront", "dtw_generic", "pair_cost", "compare",
-        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc", "dtw_backtrack", "normalize_pose"};
+        "bf16_front", "bf16_aggregate", "bf16_gemm_gcn", "bf16_gemm_tcn1x1", "bf16_tconv", "bf16_misc", "dtw_backtrack", "normalize_pose",
+        "embed_encoder", "embed_cost_gemm"};
     return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 
@@ -215,6 +216,7 @@ void free_ctx(Ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->bf16) bf16_path_destroy(ctx);
+    align_embed_destroy(ctx);
     void *ptrs[] = {ctx->headWT, ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
                     ctx->bufU[1], ctx->PT, ctx->PV, ctx->PVpart, ctx->seS, ctx->gT, ctx->gV, ctx->d_skel,
                     ctx->d_logits, ctx->d_labels, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
@@ -585,6 +587,36 @@ int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, in
     if ((rc = mark_done(ctx, sc))) return rc;
     GS_CUDA(cudaStreamSynchronize(sc));
     return GS_OK;
+}
+
+int gs_set_align_encoder(gs_ctx *h, const float *blob_host, size_t nbytes) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx || !blob_host || nbytes % 4) {
+        set_error("gs_set_align_encoder: ctx / blob missing or size not a multiple of 4");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    return align_embed_set_encoder(ctx, blob_host, nbytes / 4);
+}
+
+int gs_align_embed(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, int Tb, int V, int Cc,
+                   float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, float *cost_matrix_dev, void *cuda_stream) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!cost_dev || ((path_dev == nullptr) != (path_len_dev == nullptr))) {
+        set_error("cost_dev must be set; path_dev and path_len_dev must both be set or both NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if ((rc = order_after_previous(ctx, st))) return rc;
+    GS_CUDA(cudaEventRecord(ctx->ev_start, st));
+    rc = align_embed_launch(ctx, a_dev, b_dev, N, Ta, Tb, V, Cc, cost_dev, path_dev, path_len_dev, cost_matrix_dev, st);
+    if (rc) return rc;
+    GS_CUDA(cudaEventRecord(ctx->ev_stop, st));
+    ctx->ev_valid = true;
+    return mark_done(ctx, st);
 }
 
 int gs_pair_cost(gs_ctx *h, const float *a_dev, const float *b_dev, int N, int Ta, int Tb, int V, int Cc,

@@ -51,12 +51,14 @@ struct BlockParams {
 };
 
 struct Bf16Path;   // segment_bf16.cu
+struct EmbedPath;  // align_embed.cu
 
 // ---- per-kernel profiling (bench.py roofline): CUDA events around each launch ----
 enum KernelId {
     K_AGG = 0, K_GEMM_GCN, K_GEMM_TCN1, K_GEMM_RES, K_TCONV, K_STATS, K_SE, K_STJ, K_HEAD, K_FEAT,
     K_DTW, K_DTW_GENERIC, K_PAIRCOST, K_COMPARE,
     K_B_FRONT, K_B_AGG, K_B_GEMM_GCN, K_B_GEMM_TCN1, K_B_TCONV, K_B_MISC, K_DTW_BACKTRACK, K_POSE,
+    K_EMBED, K_EMBED_COST,
     K_COUNT
 };
 const char *kernel_name(int id);
@@ -133,6 +135,7 @@ struct Ctx {
     cudaStream_t last_stream = nullptr;
 
     Bf16Path *bf16 = nullptr;
+    EmbedPath *embed = nullptr;          // align_embed.cu
     Profiler prof;
 };
 
@@ -175,10 +178,20 @@ int cached_occupancy(Ctx *ctx, const void *kernel, int nthreads, size_t smem_byt
 int align_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
                  float *cost, int32_t *path, int32_t *plen, cudaStream_t st, const uint8_t *la = nullptr,
                  const uint8_t *lb = nullptr, float penalty = 0.f);
+int backtrack_launch(Ctx *ctx, const uint32_t *dirs, int N, int ra, int rb, bool swap, int32_t *path, int32_t *plen,
+                     cudaStream_t st);
+int dtw_costmat_launch(Ctx *ctx, const float *cm, int N, int ra, int rb, bool swap, float *cost, int32_t *path,
+                       int32_t *plen, cudaStream_t st);
 int pair_cost_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc,
                      float *out, cudaStream_t st);
 int compare_launch(Ctx *ctx, const float *a, const float *b, const int32_t *path, const int32_t *plen,
                    int N, int Ta, int Tb, int V, int Cc, float *out, cudaStream_t st);
+
+// align_embed.cu: learned alignment embedding (encoder -> tensor-core cost matrix -> DP)
+int align_embed_set_encoder(Ctx *ctx, const float *blob, size_t nfloats);
+int align_embed_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, int Tb, int V, int Cc, float *cost,
+                       int32_t *path, int32_t *plen, float *cost_matrix_out, cudaStream_t st);
+void align_embed_destroy(Ctx *ctx);
 
 // pose.cu
 int normalize_pose_launch(Ctx *ctx, const float *kp, float *out, int B, int T, int V, float min_score,

@@ -32,7 +32,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}
 ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
     "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-    "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
+    "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
     "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
 
@@ -92,6 +92,8 @@ def load_library():
         L.gs_compare.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_normalize_pose.argtypes = [vp, vp, vp, i32, i32, i32, ctypes.c_float, vp]
         L.gs_align_phase.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.gs_set_align_encoder.argtypes = [vp, vp, ctypes.c_size_t]
+        L.gs_align_embed.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.gs_launch_count.argtypes = [vp]
         L.gs_launch_count.restype = ctypes.c_int64
         L.gs_workspace_bytes.argtypes = [vp]
@@ -112,7 +114,7 @@ def load_library():
             getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
-                     "gs_compare", "gs_normalize_pose", "gs_align_phase"):
+                     "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed"):
             getattr(L, name).restype = ctypes.c_int
         if L.gs_abi_version() != 1:
             raise GolferError("libgolfer_b200.so ABI version mismatch")
@@ -527,3 +529,41 @@ def align_phase(a, b, labels_a, labels_b, penalty: float, ctx: Optional[Context]
                                      path.data_ptr() if want_path else None,
                                      plen.data_ptr() if want_path else None, _stream_ptr(torch)), "gs_align_phase")
     return cost, path, plen
+
+
+class EmbedAligner:
+    """Learned alignment embedding (C ABI gs_set_align_encoder / gs_align_embed): a per-frame
+    encoder, the frame-to-frame cost as a tensor-core GEMM of the embeddings, then the DTW of `align`.
+    `blob`: fp32 {W1 [34,128], b1, W2 [128,128], b2} (AlignEmbedConfig v0; the reference ships neither encoder nor
+    loss, so the weights are the caller's - the tests and the bench use seeded random ones)."""
+
+    def __init__(self, blob: np.ndarray, device: int = 0):
+        self.ctx = Context(device)
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _check(self.ctx._L.gs_set_align_encoder(self.ctx.handle, blob.ctypes.data, blob.nbytes), "gs_set_align_encoder")
+
+    def align(self, a, b, want_path: bool = True, want_cost_matrix: bool = False):
+        """a [N,Ta,17,Cc], b [N,Tb,17,Cc] CUDA fp32 -> (cost [N], path [N,Ta+Tb-1,2] (-1 padded), path_len [N]
+        [, cost matrix [N,max(Ta,Tb),min(Ta,Tb)]: rows = frames of the LONGER sequence])."""
+        torch = _torch()
+        dev = self.ctx.device
+        a = _dev_tensor(torch, a, "a", dev, torch.float32)
+        b = _dev_tensor(torch, b, "b", dev, torch.float32)
+        if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+            raise GolferError(f"align expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
+        N, Ta, V, Cc = (int(s) for s in a.shape)
+        Tb = int(b.shape[1])
+        if Cc < 2 or Ta < 1 or Tb < 1:
+            raise GolferError("align needs (x, y) channels and at least one frame per sequence")
+        cost = torch.empty((N,), dtype=torch.float32, device=a.device)
+        path = torch.empty((N, Ta + Tb - 1, 2), dtype=torch.int32, device=a.device) if want_path else None
+        plen = torch.empty((N,), dtype=torch.int32, device=a.device) if want_path else None
+        cm = torch.empty((N, max(Ta, Tb), min(Ta, Tb)), dtype=torch.float32, device=a.device) if want_cost_matrix else None
+        if N:
+            with torch.cuda.device(dev):
+                _check(self.ctx._L.gs_align_embed(self.ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc,
+                                                  cost.data_ptr(), path.data_ptr() if want_path else None,
+                                                  plen.data_ptr() if want_path else None,
+                                                  cm.data_ptr() if want_cost_matrix else None, _stream_ptr(torch)),
+                       "gs_align_embed")
+        return (cost, path, plen, cm) if want_cost_matrix else (cost, path, plen)

@@ -188,3 +188,25 @@ def pack_blob(cfg: GolfSegConfig, p: Dict[str, np.ndarray]) -> np.ndarray:
 
 def blob_sha256(blob: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(blob).tobytes()).hexdigest()
+
+
+# ---- learned alignment embedding: AlignEmbedConfig v0 -------------------------------------
+# [ASSUMPTION] per-frame MLP over the (x, y) of the 17 joints: 34 -> 128 (ReLU) -> 128.  The reference trains its
+# alignment model (README.md:44-47 shows a loss curve) but ships neither encoder nor loss, so these are seeded
+# random weights; the CPU oracle (oracle/embed.py) and the CUDA library consume the same dictionary.
+EMBED_IN, EMBED_HIDDEN, EMBED_DIM = 34, 128, 128
+
+
+def make_embed_params(seed: int = 4321) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(seed)
+    return {
+        "W1": (rng.standard_normal((EMBED_IN, EMBED_HIDDEN)) * np.sqrt(2.0 / EMBED_IN)).astype(np.float32),
+        "b1": rng.normal(0, 0.05, EMBED_HIDDEN).astype(np.float32),
+        "W2": (rng.standard_normal((EMBED_HIDDEN, EMBED_DIM)) * np.sqrt(1.0 / EMBED_HIDDEN)).astype(np.float32),
+        "b2": rng.normal(0, 0.05, EMBED_DIM).astype(np.float32),
+    }
+
+
+def pack_embed_blob(p: Dict[str, np.ndarray]) -> np.ndarray:
+    """Host blob handed to gs_set_align_encoder: W1 [34,128], b1 [128], W2 [128,128], b2 [128], fp32, in this order."""
+    return np.concatenate([np.ascontiguousarray(p[k], dtype=np.float32).ravel() for k in ("W1", "b1", "W2", "b2")])

@@ -125,6 +125,21 @@ int gs_align_phase(gs_ctx *ctx, const float *a_dev, const float *b_dev, const ui
                    const uint8_t *labels_b_dev, float penalty, int N, int Ta, int Tb, int V, int Cc,
                    float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, void *cuda_stream);
 
+/* Learned alignment embedding (/root/reference/README.md:44-47: the alignment model is
+ * trained).  Contract: oracle/embed.py, AlignEmbedConfig v0 - a per-frame MLP 34 -> 128 (ReLU) -> 128 over the
+ * (x, y) of V = 17 joints, frame cost c[i,j] = sqrt(max(|fa_i|^2 + |fb_j|^2 - 2 fa_i.fb_j, 0)) (the embeddings
+ * rounded to bf16, the Gram term on tcgen05 tensor cores with fp32 accumulation), then the DP, tie-break and
+ * backtrack of gs_align.
+ * gs_set_align_encoder: host fp32 blob {W1 [34,128], b1 [128], W2 [128,128], b2 [128]} (oracle/embed.py:
+ *   pack_embed_blob), copied to the device; may be called again to replace the weights.
+ * gs_align_embed: as gs_align; cost_matrix_dev (may be NULL) additionally receives the cost matrices, [N,Ta,Tb]
+ *   fp32 when Ta >= Tb and [N,Tb,Ta] (transposed) when Ta < Tb.  Parity: cost matrix within 1e-2 relative of the
+ *   fp32 oracle; total and path bit-exact against the oracle's DP on that cost matrix. */
+int gs_set_align_encoder(gs_ctx *ctx, const float *blob_host, size_t nbytes);
+int gs_align_embed(gs_ctx *ctx, const float *a_dev, const float *b_dev, int N, int Ta, int Tb, int V, int Cc,
+                   float *cost_dev, int32_t *path_dev, int32_t *path_len_dev, float *cost_matrix_dev,
+                   void *cuda_stream);
+
 /* Same through HOST buffers (copies inside; returns when results are on the host). */
 int gs_align_host(gs_ctx *ctx, const float *a_host, const float *b_host, int N, int Ta,
                   int Tb, int V, int Cc, float *cost_host, int32_t *path_host,
