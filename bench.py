@@ -545,20 +545,29 @@ def main():
         traffic = None
         if os.path.exists(TRAFFIC_JSON) and B == BATCH:
             traffic = json.load(open(TRAFFIC_JSON)).get(top, {}).get("bytes_per_launch")
-        tensor_bound = "gemm" in top or "tconv" in top
-        if tensor_bound:
+        # which roof bounds this kernel: the slower of its two floors (algorithmic flops at the sustained bf16 peak,
+        # algorithmic bytes at the measured copy bandwidth); `frac` = that floor / the measured time
+        t_s = tv["ms"] * 1e-3
+        floor_tensor = tv["flops"] / (peaks["tf_sust"] * 1e12)
+        floor_hbm = tv["bytes"] / (peaks["hbm"] * 1e9)
+        common = {"kernel": top, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r2_traffic.json)",
+                  "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                  "algorithmic_flops_per_launch": tv["flops"] / tv["launches"],
+                  "frac_of_tensor_roof": floor_tensor / t_s, "frac_of_hbm_roof": floor_hbm / t_s}
+        if floor_tensor >= floor_hbm:
             ach = tv["flops"] / tv["ms"] / 1e9
-            peak = peaks["tf_sust"]
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
-                        "peak_source": f"{peaks['source']} bf16 sustained"}
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf_sust"], "peak_source": f"{peaks['source']} bf16 sustained", **common}
         else:
             ach = tv["bytes"] / tv["ms"] / 1e6
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
-                        "peak_source": f"{peaks['source']} copy"}
+            roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm"], "peak_source": f"{peaks['source']} copy", **common}
+        # the same for every kernel of the step, so the second-largest one is judged on its own roof too
+        for name, v in prof.items():
+            if v["ms"] > 0:
+                ft, fh = v["flops"] / (peaks["tf_sust"] * 1e12), v["bytes"] / (peaks["hbm"] * 1e9)
+                kernels[name]["bound"] = "tensor" if ft >= fh else "hbm"
+                kernels[name]["roof_frac"] = max(ft, fh) / (v["ms"] * 1e-3)
     whole_net = {
         "tflops": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 * world / world,
         "frac_of_tensor_peak": cfg.flops_per_clip(T_FRAMES) * B * K / (seg_ms * 1e-3) / 1e12 / peaks["tf_sust"],

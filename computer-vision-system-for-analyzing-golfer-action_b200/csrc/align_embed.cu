@@ -29,10 +29,12 @@ namespace {
 
 using namespace tc;
 
-constexpr int kEncFrames = 64;        // frames per CTA of the encoder
+constexpr int kEncFrames = 128;       // frames per CTA pass of the encoder
+constexpr int kEncThreads = 512;      // 32 frame groups x 16 output groups: 4 frames x 8 outputs per thread
 
-// smem: W1 [34][128], b1[128], W2 [128][128], b2[128], x [64][34], h [64][128 + 4]
-__global__ void __launch_bounds__(256)
+// smem: W1 [34][128], b1[128], W2 [128][128], b2[128], x [128][34], h [128][128 + 4]: 166 KB, 16 warps per SM (the
+// 8-warp form ran at 28 % of the FMA pipe: shared-memory latency with nothing to hide it)
+__global__ void __launch_bounds__(kEncThreads)
 embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nframes, const float *__restrict__ W1,
                      const float *__restrict__ b1, const float *__restrict__ W2, const float *__restrict__ b2,
                      __nv_bfloat16 *__restrict__ F, float *__restrict__ norm) {
@@ -40,8 +42,8 @@ embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nfr
     float *sW1 = sm, *sb1 = sW1 + kEmbIn * kEmbHidden, *sW2 = sb1 + kEmbHidden, *sb2 = sW2 + kEmbHidden * kEmbDim;
     float *sx = sb2 + kEmbDim, *sh = sx + kEncFrames * kEmbIn;
     constexpr int ldh = kEmbHidden + 4;
-    for (int e = threadIdx.x; e < kEmbIn * kEmbHidden; e += 256) sW1[e] = W1[e];
-    for (int e = threadIdx.x; e < kEmbHidden * kEmbDim; e += 256) sW2[e] = W2[e];
+    for (int e = threadIdx.x; e < kEmbIn * kEmbHidden; e += kEncThreads) sW1[e] = W1[e];
+    for (int e = threadIdx.x; e < kEmbHidden * kEmbDim; e += kEncThreads) sW2[e] = W2[e];
     if (threadIdx.x < kEmbHidden) {
         sb1[threadIdx.x] = b1[threadIdx.x];
         sb2[threadIdx.x] = b2[threadIdx.x];
@@ -50,7 +52,7 @@ embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nfr
     for (size_t f0 = (size_t)blockIdx.x * kEncFrames; f0 < nframes; f0 += (size_t)gridDim.x * kEncFrames) {
         __syncthreads();
         const int nf = (int)(nframes - f0 < (size_t)kEncFrames ? nframes - f0 : (size_t)kEncFrames);
-        for (int e = threadIdx.x; e < kEncFrames * kEmbIn; e += 256) {
+        for (int e = threadIdx.x; e < kEncFrames * kEmbIn; e += kEncThreads) {
             const int f = e / kEmbIn, k = e - f * kEmbIn;          // k = joint * 2 + (x | y)
             sx[e] = f < nf ? frames[((f0 + f) * V + (k >> 1)) * Cc + (k & 1)] : 0.f;
         }
@@ -60,6 +62,7 @@ embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nfr
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int o = 0; o < 8; ++o) acc[a][o] = sb1[og * 8 + o];
+#pragma unroll 2
         for (int k = 0; k < kEmbIn; ++k) {
             const float4 w0 = *reinterpret_cast<const float4 *>(sW1 + k * kEmbHidden + og * 8);
             const float4 w1 = *reinterpret_cast<const float4 *>(sW1 + k * kEmbHidden + og * 8 + 4);
@@ -80,6 +83,7 @@ embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nfr
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int o = 0; o < 8; ++o) acc[a][o] = sb2[og * 8 + o];
+#pragma unroll 4
         for (int k = 0; k < kEmbHidden; ++k) {
             const float4 w0 = *reinterpret_cast<const float4 *>(sW2 + k * kEmbDim + og * 8);
             const float4 w1 = *reinterpret_cast<const float4 *>(sW2 + k * kEmbDim + og * 8 + 4);
@@ -305,12 +309,12 @@ int align_embed_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, 
     if ((rc = ensure_dyn_smem(ctx, (const void *)embed_encoder_kernel, enc_smem)) != GS_OK) return rc;
     for (int which = 0; which < 2; ++which) {
         const size_t nfr = which == 0 ? rows_a : rows_b;
-        int grid = (int)((nfr + kEncFrames - 1) / kEncFrames < (size_t)ctx->sm_count * 2 ? (nfr + kEncFrames - 1) / kEncFrames
-                                                                                         : (size_t)ctx->sm_count * 2);
+        int grid = (int)((nfr + kEncFrames - 1) / kEncFrames < (size_t)ctx->sm_count ? (nfr + kEncFrames - 1) / kEncFrames
+                                                                                     : (size_t)ctx->sm_count);
         if (grid < 1) grid = 1;
         {
             LaunchScope ls(ctx, K_EMBED, st, 2.0 * nfr * (kEmbIn * kEmbHidden + kEmbHidden * kEmbDim), (double)nfr * (V * Cc * 4 + kEmbDim * 2));
-            embed_encoder_kernel<<<grid, 256, enc_smem, st>>>(which == 0 ? a : b, V, Cc, nfr, ep->W1, ep->b1, ep->W2, ep->b2,
+            embed_encoder_kernel<<<grid, kEncThreads, enc_smem, st>>>(which == 0 ? a : b, V, Cc, nfr, ep->W1, ep->b1, ep->W2, ep->b2,
                                                               ep->F + (which == 0 ? 0 : rows_a * kEmbDim),
                                                               ep->norm + (which == 0 ? 0 : rows_a));
         }

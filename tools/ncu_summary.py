@@ -59,9 +59,42 @@ def rep_table(path):
     return "\n".join(out)
 
 
+# ncu kernel name -> the name bench.py's profiler uses for it
+BENCH_NAMES = {"gcn_fused_kernel": "bf16_gemm_gcn", "tcn_fused_kernel": "bf16_tconv", "head_stream_kernel": "head",
+               "front_mma_kernel": "bf16_front", "dtw_pipeline2_kernel": "dtw_wavefront", "stj_tc_kernel": "stj_gate",
+               "se_kernel": "se_gate", "dtw_backtrack_kernel": "dtw_backtrack"}
+
+
+def traffic_json(reps, out_path, source):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel in the captures -> the JSON bench.py
+    reads for `roofline.traffic` (regenerated from the capture of THIS code state, never edited by hand)."""
+    import json
+    agg = collections.OrderedDict()
+    for path in reps:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = short(r[ki]).split("<")[0].split("::")[-1]
+            b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+            agg.setdefault(BENCH_NAMES.get(name, name), []).append(b)
+    out = {"source": source}
+    total = 0.0
+    for k, v in agg.items():
+        out[k] = {"bytes_per_launch": sum(v) / len(v), "launches": len(v),
+                  "per_launch_GB": [round(x / 1e9, 3) for x in v]}
+        total += sum(v)
+    out["total_bytes_all_captured_launches"] = total
+    json.dump(out, open(out_path, "w"), indent=1)
+    print(out_path, f"{total / 1e9:.2f} GB over the captured launches")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
+    ap.add_argument("--traffic", nargs="*", help="ncu-rep files to fold into profiles/<tag>_traffic.json")
     ap.add_argument("--launches")
     ap.add_argument("--rep")
     ap.add_argument("--cmd", default="")
@@ -77,6 +110,10 @@ def main():
                 launches_table(a.launches), ""]
     if a.rep:
         out += ["## Full capture (`--set full --clock-control none --import-source on`)", "", rep_table(a.rep), ""]
+    if a.traffic:
+        traffic_json(a.traffic, os.path.join(ROOT, "profiles", f"{a.tag}_traffic.json"),
+                     f"ncu --set full --clock-control none captures {[os.path.basename(t) for t in a.traffic]} ({a.cmd})")
+        return
     path = os.path.join(ROOT, "profiles", f"{a.tag}.md")
     open(path, "w").write("\n".join(out))
     print(path)
