@@ -27,9 +27,10 @@ struct BlockMaps {
 
 struct Bf16Path {
     std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
-    std::vector<float *> bias_t;                        // b2 (+ br)
+    std::vector<__nv_bfloat16 *> Bt1, Bt2;              // bias tiles [C][16] of the temporal kernel: b1; b2 (+ br)
     std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in fp16 fragment order (stj_tc_kernel)
     float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
+    __nv_bfloat16 *ident64 = nullptr;                   // 64x64 identity: "projection" weights of the identity residual (tcn_fused.cuh)
     std::vector<BlockMaps> maps;
     int maps_T = -1;
     bool debug_xa = false;      // GOLFER_DEBUG_XA=1: the fused GCN kernel also dumps its XA chunks into bufXA (tests/test_gpu_kernels.py)
@@ -221,15 +222,18 @@ int build_maps(Ctx *ctx, int T) {
         // temporal kernel: joint-major Y windows, (C,V,T,B) views of the [B,T,V,C] tensors
         if ((rc = tf::make_bvtc_map(&m.tf.y_win, ctx->bufY, C, T, batch, false, 64, tf::kWin))) return rc;
         if ((rc = tf::make_btvc_joint_map(&m.tf.out, ctx->bufU[i & 1], C, T, batch, 64, nout))) return rc;
-        // identity residual: block 0 adds its projected input R0, later blocks their gated input Xg
-        if ((rc = tf::make_btvc_joint_map(&m.tf.res, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, nout))) return rc;
         if ((rc = tc::make_weight_map(&m.tf.w1, bp->W1T[i], C, C, 64, 64))) return rc;
         if ((rc = tc::make_weight_map(&m.tf.w2, bp->W2p[i], crm, R * 3 * crm, crm, crm))) return rc;
-        m.tf.xg = m.tf.res;
-        m.tf.wr = m.tf.w1;
+        if ((rc = tc::make_weight_map(&m.tf.bt1, bp->Bt1[i], 16, C, 16, 64))) return rc;
+        if ((rc = tc::make_weight_map(&m.tf.bt2, bp->Bt2[i], 16, C, 16, 64))) return rc;
         if (proj) {
             if ((rc = tf::make_btvc_joint_map(&m.tf.xg, ctx->bufX, cin, T, batch, 64, tf::kWin))) return rc;
             if ((rc = tc::make_weight_map(&m.tf.wr, bp->WrT[i], cin, C, 64, 64))) return rc;
+        } else {
+            // identity residual through the tensor core: K box q of the residual source (block 0: its projected input
+            // R0, later blocks: their gated input Xg), Wr = I_64
+            if ((rc = tf::make_btvc_joint_map(&m.tf.xg, i == 0 ? ctx->bufR : ctx->bufX, C, T, batch, 64, tf::kWin))) return rc;
+            if ((rc = tc::make_weight_map(&m.tf.wr, bp->ident64, 64, 64, 64, 64))) return rc;
         }
         if (i > 0) {
             if ((rc = tc::make_weight_map(&m.wg, bp->WgT[i], 3 * cin, C, 64, C))) return rc;
@@ -289,12 +293,19 @@ int bf16_path_create(Ctx *ctx) {
             GS_CUDA(cudaMemset(bp->trace_tcn, 0, n * 8));
         }
     }
+    {
+        std::vector<__nv_bfloat16> id((size_t)64 * 64, __float2bfloat16_rn(0.f));
+        for (int k = 0; k < 64; ++k) id[(size_t)k * 64 + k] = __float2bfloat16_rn(1.f);
+        int rc0;
+        if ((rc0 = upload_bf16(ctx, id, &bp->ident64))) return rc0;
+    }
     const size_t nb = ctx->blocks.size();
     bp->WgT.assign(nb, nullptr);
     bp->W1T.assign(nb, nullptr);
     bp->W2p.assign(nb, nullptr);
     bp->WrT.assign(nb, nullptr);
-    bp->bias_t.assign(nb, nullptr);
+    bp->Bt1.assign(nb, nullptr);
+    bp->Bt2.assign(nb, nullptr);
     for (auto &v : bp->stjP) v.assign(nb, nullptr);
     const float *hb = ctx->h_blob.data();
     auto host = [&](const float *dev_ptr) { return hb + (dev_ptr - ctx->d_blob); };
@@ -353,8 +364,18 @@ int bf16_path_create(Ctx *ctx) {
                 GS_CUDA(cudaMemcpy(bp->stjP[w][i], packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
             }
         }
-        GS_CUDA(cudaMalloc((void **)&bp->bias_t[i], C * sizeof(float)));
-        GS_CUDA(cudaMemcpy(bp->bias_t[i], bias.data(), C * sizeof(float), cudaMemcpyHostToDevice));
+        // bias tiles: the bias enters the accumulator through an all-ones MMA (tcn_fused.cuh); two bf16 terms
+        auto bias_tile = [&](const float *bsrc, __nv_bfloat16 **dst) -> int {
+            std::vector<__nv_bfloat16> t((size_t)C * 16, __float2bfloat16_rn(0.f));
+            for (int n = 0; n < C; ++n) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(bsrc[n]);
+                t[(size_t)n * 16] = hi;
+                t[(size_t)n * 16 + 1] = __float2bfloat16_rn(bsrc[n] - __bfloat162float(hi));
+            }
+            return upload_bf16(ctx, t, dst);
+        };
+        if ((rc = bias_tile(host(b.b1), &bp->Bt1[i]))) return rc;
+        if ((rc = bias_tile(bias.data(), &bp->Bt2[i]))) return rc;
         if (i == 0) {   // block 0 on warp-level tensor cores (front_mma_kernel)
             std::vector<float> bm;
             pack_front_matrix(host(b.Wg), host(b.bg), host(b.Wr), host(b.br), C, bm);
@@ -369,15 +390,14 @@ int bf16_path_create(Ctx *ctx) {
 void bf16_path_destroy(Ctx *ctx) {
     Bf16Path *bp = ctx->bf16;
     if (!bp) return;
-    for (auto *v : {&bp->WgT, &bp->W1T, &bp->W2p, &bp->WrT})
+    for (auto *v : {&bp->WgT, &bp->W1T, &bp->W2p, &bp->WrT, &bp->Bt1, &bp->Bt2})
         for (__nv_bfloat16 *p : *v)
             if (p) cudaFree(p);
-    for (float *p : bp->bias_t)
-        if (p) cudaFree(p);
     for (auto &v : bp->stjP)
         for (float *p : v)
             if (p) cudaFree(p);
     if (bp->frontB) cudaFree(bp->frontB);
+    if (bp->ident64) cudaFree(bp->ident64);
     if (bp->trace) cudaFree(bp->trace);
     if (bp->trace_tcn) cudaFree(bp->trace_tcn);
     delete bp;
@@ -475,8 +495,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             memset(&q, 0, sizeof(q));
             q.B = B; q.T = T; q.C = C; q.cr = cr; q.cin = cin;
             q.nbr = 64 / cr;
-            q.proj = proj ? 1 : 0;
-            q.nkx = proj ? cin / 64 : 0;
+            q.res_q = proj ? 0 : 1;
+            q.nkx = proj ? cin / 64 : 1;
             q.nky = C / 64;
             q.dmax = 1;
             for (int r = 0; r < R; ++r) {
@@ -487,8 +507,6 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.ttiles = cdiv(T, q.nout);
             q.nboxes = C / 64;
             q.nq_items = B * q.ttiles;
-            q.bias1 = b.b1;
-            q.bias = bp->bias_t[i];
             q.PT = ctx->PT;
             q.PVpart = ctx->PVpart;
             q.trace = bp->trace_tcn ? bp->trace_tcn + (size_t)i * 4 * tf::kTrSteps * tf::kTrEv : nullptr;

@@ -3,7 +3,10 @@
 //   H[b,t,v, :]       = relu(Y[b,t,v, :] . W1 + b1)                         zero outside [0,T)
 //   U[b,t,v, r*cr+co] = relu( sum_{j<3, ci<cr} H[b, t+(j-1)d_r, v, r*cr+ci] * W2[r,j,ci,co] + b2
 //                             + residual[b,t,v, r*cr+co] )
-//   residual = the block's gated input (identity) or its 1x1 projection Xg . Wr (width change)
+//   residual = the block's gated input (identity) or its 1x1 projection Xg . Wr (width change); BOTH run through
+//   the tensor core into the U accumulator: the identity as Xg[:, box q] . I_64 (1.0 * x is exact in the fp32
+//   accumulator).  Adding the residual box in the epilogue instead (a TMA load per step into the staging slot, an
+//   unpack and 16 adds per thread) measured 7-20 % slower per launch: the epilogue warps are the bound.
 // Stage replaced: /root/reference/README.md:29-30 (Temporal Module - Multi-branch Temporal Convolution).
 //
 // H never reaches HBM (round 1 ran the 1x1 as its own GEMM: one write and one read of a [rows, C]
@@ -14,14 +17,16 @@
 //     128-frame window [t0-dmax, t0+128-dmax) of Y, all C channels, as C/64 TMA boxes that stream
 //     through a ring; frames outside [0,T) are zero-filled by TMA;
 //   * MMA A (tcgen05, SS): Hacc[128 x 64] = Ywin[128 x C] . W1[:, box q]      (W1 slice resident in smem)
-//   * the step's epilogue group turns Hacc into the bf16, 128B-swizzled K-major box Hbox (+b1, ReLU,
-//     rows whose frame lies outside [0,T) forced to zero = the conv's zero padding);
+//   * both biases enter through the tensor core as well: one extra K = 16 MMA per accumulator whose A operand is a
+//     resident all-ones tile and whose B operand holds the bias split into two bf16 terms (hi + lo, 2^-17 relative)
+//     in its first two K columns: 32 FADDs per thread and step less in the warps that bound the kernel;
+//   * the step's epilogue group turns Hacc into the bf16, 128B-swizzled K-major box Hbox (ReLU inside the
+//     bf16x2 conversion, rows whose frame lies outside [0,T) forced to zero = the conv's zero padding);
 //   * MMA B: the 3 taps of every branch in the box are MMAs whose A descriptors start at ROW offsets
 //     dmax+(j-1)d inside Hbox (the swizzle is a function of the absolute smem address: any row offset
 //     works), accumulator row m = frame t0+m; rows m >= 128-2*dmax read past the window and are
 //     discarded, so a tile yields nout = 128-2*dmax output frames;
-//   * epilogue: +b2, + residual box (TMA-loaded into the staging slot) or the projection MMAs' sum,
-//     ReLU, bf16, TMA store; frame-pooling sums PT stay in registers over the 17 joints of an item,
+//   * epilogue: ReLU (bias and residual are already in the accumulator), bf16, TMA store; frame-pooling sums PT stay in registers over the 17 joints of an item,
 //     joint-pooling partials PVpart are column sums of each staged tile (SE / ST-joint attention).
 // A CTA owns one output box (its W1 slice, tap and projection weights stay resident) and walks its
 // (clip, frame-tile) items joint by joint.  The 16 epilogue warps run convert(step n), then
@@ -30,8 +35,7 @@
 // Warp roles (576 threads, 1 CTA/SM): w0 TMA producer (Y windows, projection-input boxes), w1 TMEM alloc +
 // MMA issuer, w2-17 epilogue warps (TMEM lanes = rows by w%4, 16 of the box's 64 columns by (w-2)/4: 16
 // pooling sums + a 16-column accumulator slice per thread keep the row math inside 96 registers).  The
-// leader epilogue thread issues the TMA stores and the identity-residual box loads (two steps ahead, into
-// the staging slot whose store it has just drained).
+// leader epilogue thread issues the TMA stores.
 // TMEM (256 columns): [0,128) two 64-column U accumulators, [128,192) Hacc.
 //
 // Measured and kept out (all parity-green, experiments/tcn_fused_decoupled.cuh.txt): hand-overs through
@@ -57,16 +61,15 @@ constexpr uint32_t kBoxBytes = 16384;   // 128 rows x 64 bf16
 struct Params {
     int B, T, C, cr, cin;
     int nbr;          // branches inside one 64-channel box (64 / cr)
-    int proj;         // 1: residual = Xg . Wr (extra MMAs), 0: identity residual box added in the epilogue
-    int nkx;          // projection K boxes (cin / 64)
+    int res_q;        // 0: residual = Xg . Wr (cin / 64 K boxes); 1: identity residual: the only K box is channel box q
+                      //    of the block input and Wr is the 64x64 identity
+    int nkx;          // residual K boxes (cin / 64; 1 with res_q)
     int nky;          // 1x1 K boxes (C / 64)
     int dil[GS_MAX_BRANCHES];
     int dmax, nout;   // largest dilation; output frames per tile = 128 - 2*dmax
     int ttiles, nboxes, nq_items;   // frame tiles per clip, 64-channel boxes, items per box (B * ttiles)
-    int slots, eslots;   // ring depth (boxes); staging slots (2 or 3)
-    uint32_t w1_off, w2_off, wr_off, w1_bytes, w2_bytes, wr_bytes, hbox_off, hbox_span, out_off, scr_off, bar_off, total;
-    const float *bias1;   // [C]  b1 (folded BN of the 1x1)
-    const float *bias;    // [C]  b2 (+ folded projection bias)
+    int slots, eslots;   // ring depth (boxes); staging slots (2)
+    uint32_t w1_off, w2_off, wr_off, w1_bytes, w2_bytes, wr_bytes, bias_off, hbox_off, hbox_span, out_off, scr_off, bar_off, total;
     float *PT;            // [B,T,C]
     float *PVpart;        // [B,ttiles,17,C]
     unsigned long long *trace;   // optional clock64 trace of CTA 0 (GOLFER_TRACE_TCN=1, tools/trace_tcn.py)
@@ -89,12 +92,12 @@ constexpr int kTrSteps = 8, kTrEv = 16, kTrFirst = 20;
 
 struct Maps {
     CUtensorMap y_win;    // Y joint-major [B,V,T,C]: box (64 ch, 128 frames, 1 joint, 1 clip)
-    CUtensorMap xg;       // Xg [B,T,V,cin] seen as (C, V, T, B): box (64 ch, 1 joint, 128 frames, 1)  (projection input)
-    CUtensorMap res;      // identity residual [B,T,V,C]: box (64 ch, 1 joint, nout frames, 1)
+    CUtensorMap xg;       // residual source Xg [B,T,V,cin] seen as (C, V, T, B): box (64 ch, 1 joint, 128 frames, 1)
     CUtensorMap out;      // U [B,T,V,C], same box shape
     CUtensorMap w1;       // 1x1 weights W1T [C n][C k]: box (64 k, 64 n)
     CUtensorMap w2;       // tap weights [(r*3+j)*cr + co][ci], box (cr, cr)
-    CUtensorMap wr;       // projection weights [C][cin], box (64 k, 64 n)
+    CUtensorMap wr;       // projection weights [C][cin] (or the 64x64 identity), box (64 k, 64 n)
+    CUtensorMap bt1, bt2; // bias tiles [C][16]: column 0 = bf16(b), column 1 = bf16(b - column 0), rest 0; box (16 k, 64 n)
 };
 
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
@@ -124,9 +127,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
     uint64_t *hempty = hfull + 1;                // Hacc read by the epilogue warps
     uint64_t *hready = hempty + 1;               // Hbox written and visible to the async proxy
     uint64_t *wres = hready + 1;
-    uint64_t *res_full = wres + 1;               // [3 staging slots] residual box landed (identity blocks)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_full + 3);
-    float *sbias = reinterpret_cast<float *>(smem + prm.bar_off + 512);    // [64] b2, then [64] b1
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wres + 1);
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int SLOTS = prm.slots, ES = prm.eslots;
@@ -140,11 +141,12 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.y_win);
         tma_prefetch_desc(&maps.xg);
-        tma_prefetch_desc(&maps.res);
         tma_prefetch_desc(&maps.out);
         tma_prefetch_desc(&maps.w1);
         tma_prefetch_desc(&maps.w2);
         tma_prefetch_desc(&maps.wr);
+        tma_prefetch_desc(&maps.bt1);
+        tma_prefetch_desc(&maps.bt2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kTfMaxSlots; ++s) {
@@ -158,13 +160,15 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         mbar_init(hfull, 1);
         mbar_init(hempty, kTfEpi);
         mbar_init(hready, kTfEpi);
-        for (int s = 0; s < 3; ++s) mbar_init(&res_full[s], 1);
         mbar_init(wres, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
-    if (threadIdx.x < 64) sbias[threadIdx.x] = prm.bias[q * 64 + threadIdx.x];
-    else if (threadIdx.x < 128) sbias[threadIdx.x] = prm.bias1[q * 64 + threadIdx.x - 64];
+    // the all-ones A tile of the bias MMAs: [128 rows][16 k] bf16, 32-byte rows (invariant under the 32B swizzle)
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 256)
+        *reinterpret_cast<uint4 *>(smem + prm.bias_off + (size_t)(threadIdx.x - 64) * 16) =
+            make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -179,15 +183,17 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         // ===== producer: weights once, then per step the C/64 Y-window boxes (and, projection blocks, the cin/64
         // input boxes of the PREVIOUS step), in the order the MMA issuer consumes them: A(0) [A(1) B(0)] [A(2) B(1)] ...
         if (elect_one()) {
-            mbar_expect_tx(wres, prm.w1_bytes + prm.w2_bytes + prm.wr_bytes);
+            mbar_expect_tx(wres, prm.w1_bytes + prm.w2_bytes + prm.wr_bytes + 4096u);
+            tma_load_2d(smem + prm.bias_off + 4096, &maps.bt1, wres, 0, q * 64);
+            tma_load_2d(smem + prm.bias_off + 6144, &maps.bt2, wres, 0, q * 64);
             for (int kb = 0; kb < prm.nky; ++kb)
                 tma_load_2d(smem + prm.w1_off + (size_t)kb * 8192, &maps.w1, wres, kb * 64, q * 64);
             for (int rl = 0; rl < NBR; ++rl)
                 for (int j = 0; j < 3; ++j)
                     tma_load_2d(smem + prm.w2_off + (size_t)(rl * 3 + j) * (CRM * CRM * 2), &maps.w2, wres, 0,
                                 ((q * NBR + rl) * 3 + j) * CRM);
-            for (int kx = 0; kx < (prm.proj ? prm.nkx : 0); ++kx)
-                tma_load_2d(smem + prm.wr_off + (size_t)kx * 8192, &maps.wr, wres, kx * 64, q * 64);
+            for (int kx = 0; kx < prm.nkx; ++kx)
+                tma_load_2d(smem + prm.wr_off + (size_t)kx * 8192, &maps.wr, wres, kx * 64, prm.res_q ? 0 : q * 64);
         }
         __syncwarp();
         int slot = 0;
@@ -203,7 +209,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 if (elect_one()) {
                     mbar_expect_tx(&full[slot], kBoxBytes);
                     if (which == 0) tma_load_4d(sa, &maps.y_win, &full[slot], kb * 64, t0 - prm.dmax, v, b);
-                    else tma_load_4d(sa, &maps.xg, &full[slot], kb * 64, v, t0, b);
+                    else tma_load_4d(sa, &maps.xg, &full[slot], prm.res_q ? q * 64 : kb * 64, v, t0, b);
                 }
                 __syncwarp();
                 if (++slot == SLOTS) { slot = 0; phase ^= 1; }
@@ -211,7 +217,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         };
         if (nsteps > 0) load_boxes(0, 0);
         for (int st = 0; st < nsteps; ++st) {
-            if (prm.proj) load_boxes(st, 1);
+            load_boxes(st, 1);
             if (st + 1 < nsteps) load_boxes(st + 1, 0);
         }
     } else if (warp == 1) {
@@ -240,6 +246,9 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w2_off + (size_t)i * (CRM * CRM * 2)), wrow_bytes);
         }
         const uint64_t dh = make_kmajor_desc(smem_u32(smem + prm.hbox_off), 128);
+        const uint64_t d_ones = make_kmajor_desc(smem_u32(smem + prm.bias_off), 32);
+        const uint64_t d_b1 = make_kmajor_desc(smem_u32(smem + prm.bias_off + 4096), 32);
+        const uint64_t d_b2 = make_kmajor_desc(smem_u32(smem + prm.bias_off + 6144), 32);
         const uint32_t th = tmem_base + kColH;
         mbar_wait(wres, 0);
         auto issue_a = [&](uint32_t n) {
@@ -247,16 +256,15 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             mbar_wait(hempty, (n & 1u) ^ 1u);
             if (lane == 0) TF_TRACE(2, n, 1);
             tc_fence_after();
+            if (elect_one()) umma_bf16(th, d_ones, d_b1, idesc_64, 0u);     // Hacc = b1
             for (int kb = 0; kb < prm.nky; ++kb) {
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
                 const uint64_t da = make_kmajor_desc(smem_u32(smem + (size_t)slot * kBoxBytes), 128);
                 const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.w1_off + (size_t)kb * 8192), 128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t accum = (uint32_t)((kb > 0) | (k > 0));
-                    if (elect_one()) umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, accum);
-                }
+                for (int k = 0; k < 4; ++k)
+                    if (elect_one()) umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
                 if (elect_one()) umma_commit(&empty[slot]);
                 __syncwarp();
                 if (++slot == SLOTS) { slot = 0; phase ^= 1; }
@@ -272,21 +280,18 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (lane == 0) TF_TRACE(2, n, 5);
             tc_fence_after();
             const uint32_t td = tmem_base + buf * 64u;
-            if (prm.proj) {
-                for (int kx = 0; kx < prm.nkx; ++kx) {
-                    mbar_wait(&full[slot], phase);
-                    tc_fence_after();
-                    const uint64_t da = make_kmajor_desc(smem_u32(smem + (size_t)slot * kBoxBytes), 128);
-                    const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.wr_off + (size_t)kx * 8192), 128);
+            if (elect_one()) umma_bf16(td, d_ones, d_b2, idesc_64, 0u);     // U = b2 (+ projection bias)
+            for (int kx = 0; kx < prm.nkx; ++kx) {
+                mbar_wait(&full[slot], phase);
+                tc_fence_after();
+                const uint64_t da = make_kmajor_desc(smem_u32(smem + (size_t)slot * kBoxBytes), 128);
+                const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.wr_off + (size_t)kx * 8192), 128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t accum = (uint32_t)((kx > 0) | (k > 0));
-                        if (elect_one()) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, accum);
-                    }
-                    if (elect_one()) umma_commit(&empty[slot]);
-                    __syncwarp();
-                    if (++slot == SLOTS) { slot = 0; phase ^= 1; }
-                }
+                for (int k = 0; k < 4; ++k)
+                    if (elect_one()) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
+                if (elect_one()) umma_commit(&empty[slot]);
+                __syncwarp();
+                if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
             mbar_wait(hready, n & 1u);
             if (lane == 0) TF_TRACE(2, n, 6);
@@ -296,13 +301,10 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 const uint64_t da = dh + (uint64_t)aoff[i];
                 const uint64_t db = dbv[i];
                 const uint32_t tdr = td + dcol[i];
-                // first tap of the first branch in a column slice overwrites, everything else accumulates
-                const uint32_t accum = (uint32_t)(prm.proj | ((i % 3) > 0) | ((((i / 3) * CR) % CRM) != 0));
+                // the bias and residual MMAs above started the accumulator: every tap accumulates
 #pragma unroll
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t acc_k = accum | (uint32_t)(k > 0);
-                    if (elect_one()) umma_bf16(tdr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tap, acc_k);
-                }
+                for (int k = 0; k < ksteps; ++k)
+                    if (elect_one()) umma_bf16(tdr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_tap, 1u);
             }
             if (elect_one()) umma_commit(&tfull[buf]);     // also: Hbox may be rewritten
             __syncwarp();
@@ -332,16 +334,12 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         const uint32_t hb0 = smem_u32(smem + prm.hbox_off) + row_off0, hb1 = smem_u32(smem + prm.hbox_off) + row_off1;
         const uint32_t out_base = smem_u32(smem + prm.out_off);
         const uint32_t a_hfull = smem_u32(hfull), a_hempty = smem_u32(hempty), a_hready = smem_u32(hready);
-        const uint32_t a_tfull = smem_u32(tfull), a_tempty = smem_u32(tempty), a_resfull = smem_u32(res_full);
+        const uint32_t a_tfull = smem_u32(tfull), a_tempty = smem_u32(tempty);
         unsigned char *sout = smem + prm.out_off;
         float *scr = reinterpret_cast<float *>(smem + prm.scr_off);    // [2][16 parts][64]
         const int c2 = gt & 31, part = gt >> 5;              // pooling: channel pair, row part (8 rows each)
         // pooling reads: 8 rows of this thread's channel pair; the swizzled chunk depends on row & 7 = k only
         const uint32_t pool_off = (uint32_t)part * 1024u + (uint32_t)(c2 & 3) * 4u;
-        float bias2[16];                                     // b2 of this thread's 16 channels (b1 is re-read: registers)
-#pragma unroll
-        for (int e = 0; e < 16; ++e) bias2[e] = sbias[cq * 16 + e];
-        const float4 *bq1 = reinterpret_cast<const float4 *>(sbias + 64 + cq * 16);
         // deferred finalisation of the previous step's joint-pooling partial sums
         int fin_b = -1, fin_tt = 0, fin_v = 0;
         auto finalize = [&](uint32_t step) {
@@ -358,16 +356,6 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                                             2 * gt) = acc;
             }
         };
-        // identity-residual box of step st -> staging slot st % ES (leader thread only; two divisions per call)
-        auto load_residual = [&](uint32_t st) {
-            const int item = cta_in_box + (int)(st / 17u) * ctas_per_box;
-            uint64_t *rf = &res_full[st % (uint32_t)ES];
-            mbar_expect_tx(rf, (uint32_t)nout * 128u);
-            tma_load_4d(sout + (size_t)(st % (uint32_t)ES) * kBoxBytes, &maps.res, rf, q * 64, (int)(st % 17u),
-                        (item % prm.ttiles) * nout, item / prm.ttiles);
-        };
-        if (leader && !prm.proj)
-            for (uint32_t st = 0; st < (uint32_t)ES && st < (uint32_t)nsteps; ++st) load_residual(st);
         float pt[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) pt[e] = 0.f;
@@ -375,7 +363,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         int cv = 0, c_item = cta_in_box;                     // convert: joint, item
         bool c_inside = false;
         int e_v = 0, e_item = cta_in_box, e_b = 0, e_tt = 0, e_t0 = 0, e_nvalid = 0;
-        uint32_t e_slot = 0, e_ph = 0;                       // staging slot of the epilogue step and its phase
+        uint32_t e_slot = 0;                                 // staging slot of the epilogue step
         auto item_coords = [&](int item, int &b, int &tt) { b = item / prm.ttiles; tt = item - b * prm.ttiles; };
         {
             int b0, tt0;
@@ -407,22 +395,16 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (do_cv) mbar_arrive_u32(a_hempty);
             if (do_ep) mbar_arrive_u32(a_tempty + buf * 8u);
             if (do_cv) {
-                // ---- convert(n): Hacc -> +b1, ReLU, zero outside [0,T) -> bf16 K-major Hbox
-                float bias1[16];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 t = bq1[e];
-                    bias1[4 * e] = t.x; bias1[4 * e + 1] = t.y; bias1[4 * e + 2] = t.z; bias1[4 * e + 3] = t.w;
-                }
+                // ---- convert(n): Hacc (b1 included) -> ReLU + bf16 in one conversion, zero outside [0,T) -> K-major Hbox
                 uint4 p0, p1;
-                p0.x = pack_bf16(fmaxf(__uint_as_float(acch[0]) + bias1[0], 0.f), fmaxf(__uint_as_float(acch[1]) + bias1[1], 0.f));
-                p0.y = pack_bf16(fmaxf(__uint_as_float(acch[2]) + bias1[2], 0.f), fmaxf(__uint_as_float(acch[3]) + bias1[3], 0.f));
-                p0.z = pack_bf16(fmaxf(__uint_as_float(acch[4]) + bias1[4], 0.f), fmaxf(__uint_as_float(acch[5]) + bias1[5], 0.f));
-                p0.w = pack_bf16(fmaxf(__uint_as_float(acch[6]) + bias1[6], 0.f), fmaxf(__uint_as_float(acch[7]) + bias1[7], 0.f));
-                p1.x = pack_bf16(fmaxf(__uint_as_float(acch[8]) + bias1[8], 0.f), fmaxf(__uint_as_float(acch[9]) + bias1[9], 0.f));
-                p1.y = pack_bf16(fmaxf(__uint_as_float(acch[10]) + bias1[10], 0.f), fmaxf(__uint_as_float(acch[11]) + bias1[11], 0.f));
-                p1.z = pack_bf16(fmaxf(__uint_as_float(acch[12]) + bias1[12], 0.f), fmaxf(__uint_as_float(acch[13]) + bias1[13], 0.f));
-                p1.w = pack_bf16(fmaxf(__uint_as_float(acch[14]) + bias1[14], 0.f), fmaxf(__uint_as_float(acch[15]) + bias1[15], 0.f));
+                p0.x = pack_bf16_relu(__uint_as_float(acch[0]), __uint_as_float(acch[1]));
+                p0.y = pack_bf16_relu(__uint_as_float(acch[2]), __uint_as_float(acch[3]));
+                p0.z = pack_bf16_relu(__uint_as_float(acch[4]), __uint_as_float(acch[5]));
+                p0.w = pack_bf16_relu(__uint_as_float(acch[6]), __uint_as_float(acch[7]));
+                p1.x = pack_bf16_relu(__uint_as_float(acch[8]), __uint_as_float(acch[9]));
+                p1.y = pack_bf16_relu(__uint_as_float(acch[10]), __uint_as_float(acch[11]));
+                p1.z = pack_bf16_relu(__uint_as_float(acch[12]), __uint_as_float(acch[13]));
+                p1.w = pack_bf16_relu(__uint_as_float(acch[14]), __uint_as_float(acch[15]));
                 if (!c_inside) p0 = p1 = make_uint4(0u, 0u, 0u, 0u);
                 st_shared_v4(hb0, p0);
                 st_shared_v4(hb1, p1);
@@ -441,26 +423,14 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (!do_ep) continue;
             // ---- epilogue(n-1)
             const uint32_t box_u32 = out_base + e_slot * kBoxBytes;
-            if (!prm.proj) mbar_wait_u32(a_resfull + e_slot * 8u, e_ph);   // slot holds the residual box
             if (trole >= 0) TF_TRACE(trole, n, 6);
             if (rows_live) {
                 // a warp whose 32 rows all lie past the end of the tile / clip skips the row math; it still takes
                 // part in every handshake
                 float f[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(accu[e]) + bias2[e];
-                if (!prm.proj) {
-                    const uint4 r0 = ld_shared_v4(box_u32 + row_off0), r1 = ld_shared_v4(box_u32 + row_off1);
-                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        f[2 * e] += bf16lo_to_f32(rw[e]);
-                        f[2 * e + 1] += bf16hi_to_f32(rw[e]);
-                    }
-                }
-#pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    f[e] = fmaxf(f[e], 0.f);
+                    f[e] = fmaxf(__uint_as_float(accu[e]), 0.f);
                     // frame pooling (sum over joints) of the fp32 values, as the oracle pools (the stored copy is
                     // their bf16 rounding)
                     pt[e] += f[e];
@@ -469,20 +439,14 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 st_shared_v4(box_u32 + row_off1, make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])));
             }
             fence_proxy_async_smem();
-            // projection blocks have no residual box in the slot (two slots): the store issued a step ago (the only
-            // one pending) must have read its slot before the NEXT step overwrites it; that step starts after this barrier
-            if (leader && prm.proj) tma_store_wait_read0();
+            // two staging slots: the store issued a step ago (the only one pending) must have read its slot before the
+            // NEXT step overwrites it; that step starts after this barrier
+            if (leader) tma_store_wait_read0();
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (trole >= 0) TF_TRACE(trole, n, 9);
             if (leader) {
                 tma_store_4d(&maps.out, sout + (size_t)e_slot * kBoxBytes, q * 64, e_v, e_t0, e_b);
                 tma_store_commit();
-                if (!prm.proj && m > 0) {
-                    // the previous step's store has had a whole step: once it has read its slot, the residual box of
-                    // the step that uses that slot next (ES-1 steps ahead of this one) goes in
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    if (m - 1 + (uint32_t)ES < (uint32_t)nsteps) load_residual(m - 1 + (uint32_t)ES);
-                }
             }
             // joint pooling: column sums of the staged tile over its valid frames, 16 row parts -> scratch;
             // the 16-way fold of the PREVIOUS step's scratch is published by this step's barrier
@@ -517,7 +481,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             fin_b = e_b;
             fin_tt = e_tt;
             fin_v = e_v;
-            if (++e_slot == (uint32_t)ES) { e_slot = 0; e_ph ^= 1u; }
+            if (++e_slot == (uint32_t)ES) e_slot = 0;
             if (++e_v == 17) {
                 // frame-pooling sums of this item: 16 channels of frame r, 64 contiguous bytes per thread
                 if (r < e_nvalid) {
@@ -612,12 +576,10 @@ inline bool plan(Params &p) {
     const int crm = p.cr < 16 ? 16 : p.cr;
     p.w1_bytes = (uint32_t)p.nky * 8192u;
     p.w2_bytes = (uint32_t)(p.nbr * 3 * crm * crm * 2);
-    p.wr_bytes = p.proj ? (uint32_t)p.nkx * 8192u : 0u;
+    p.wr_bytes = (uint32_t)p.nkx * 8192u;
     p.hbox_span = (((uint32_t)(kWin + 2 * p.dmax) * 128u) + 1023u) & ~1023u;
-    const uint32_t wspan = p.w1_bytes + ((p.w2_bytes + 1023u) & ~1023u) + p.wr_bytes;
-    // identity blocks: three staging slots give the residual box two steps of lookahead (its TMA latency is
-    // about one step); projection blocks have no residual box and take two
-    const int es_hi = p.proj ? 2 : 3, es_lo = 2;
+    const uint32_t wspan = p.w1_bytes + ((p.w2_bytes + 1023u) & ~1023u) + p.wr_bytes + 8192u /*ones + bias tiles*/;
+    const int es_hi = 2, es_lo = 2;
     for (int min_slots = 4; min_slots >= 2; --min_slots) {
         for (int es = es_hi; es >= es_lo; --es) {
             const uint32_t fixed = wspan + p.hbox_span + (uint32_t)es * kBoxBytes + 8192u /*pooling scratch*/ +
@@ -630,6 +592,7 @@ inline bool plan(Params &p) {
             p.w1_off = (uint32_t)st * kBoxBytes;
             p.w2_off = p.w1_off + p.w1_bytes;
             p.wr_off = p.w2_off + ((p.w2_bytes + 1023u) & ~1023u);
+            p.bias_off = p.wr_off + p.wr_bytes;
             p.hbox_off = p.w1_off + wspan;
             p.out_off = p.hbox_off + p.hbox_span;
             p.scr_off = p.out_off + (uint32_t)es * kBoxBytes;

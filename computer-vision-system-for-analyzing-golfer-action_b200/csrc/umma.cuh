@@ -207,6 +207,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// max(x, 0) and the bf16x2 rounding in ONE conversion (a -> low half, b -> high half, as pack_bf16)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+
 // ------------------------------------------------------------------ host side ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
