@@ -176,3 +176,16 @@ def test_phase_penalty_keeps_the_path_inside_matching_phases():
     assert cost >= plain_cost
     # the unconstrained optimum crosses phases here, so the constraint really binds
     assert np.any(la[plain_path[:, 0]] != lb[plain_path[:, 1]])
+
+
+def test_division_by_17_in_three_operations_is_the_ieee_quotient(tmp_path):
+    """The DTW cost producers divide the joint sum by V = 17 as q0 = x * rc, r = fma(-17, q0, x), q = fma(r, rc, q0)
+    (csrc/align.cu:div17_exact) instead of a full division.  tools/div17_check.c compares that with x / 17 for
+    every normal float32 (45 s); this runs every 211th value of both signs (20 M values)."""
+    import subprocess
+    exe = tmp_path / "div17_check"
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "div17_check.c")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), src, "-lm"], check=True)
+    out = subprocess.run([str(exe), "211"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches 0" in out.stdout
