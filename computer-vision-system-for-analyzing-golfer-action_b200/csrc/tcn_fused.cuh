@@ -36,7 +36,10 @@
 // MMA issuer, w2-17 epilogue warps (TMEM lanes = rows by w%4, 16 of the box's 64 columns by (w-2)/4: 16
 // pooling sums + a 16-column accumulator slice per thread keep the row math inside 96 registers).  The
 // leader epilogue thread issues the TMA stores.
-// TMEM (256 columns): [0,128) two 64-column U accumulators, [128,192) Hacc.
+// TMEM (256 columns): [0,128) two 64-column U accumulators, [128,256) two 64-column Hacc buffers.  With ONE Hacc the
+// issuer's work sat inside the loop that paced the kernel (trace at C = 256: convert(n) done -> 12 tap MMAs issued
+// 365 cycles -> the 17 MMAs of A(n+1) issued 900 cycles, 52 per MMA -> completion 350 -> TMEM load + convert(n+1)
+// 750 = the 2600-cycle step); with two, A(n+2) is issued behind B(n) and is complete long before convert(n+2) asks.
 //
 // Measured and kept out (all parity-green, experiments/tcn_fused_decoupled.cuh.txt): hand-overs through
 // mbarriers only (no CTA barrier per step, a store warp, shuffle-reduced pooling), two issuer warps with a
@@ -123,9 +126,9 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
     uint64_t *empty = full + kTfMaxSlots;
     uint64_t *tfull = empty + kTfMaxSlots;       // [2 U accumulators]
     uint64_t *tempty = tfull + 2;
-    uint64_t *hfull = tempty + 2;                // Hacc written by MMA A
-    uint64_t *hempty = hfull + 1;                // Hacc read by the epilogue warps
-    uint64_t *hready = hempty + 1;               // Hbox written and visible to the async proxy
+    uint64_t *hfull = tempty + 2;                // [2] Hacc buffer written by MMA A
+    uint64_t *hempty = hfull + 2;                // [2] Hacc buffer read by the epilogue warps
+    uint64_t *hready = hempty + 2;               // Hbox written and visible to the async proxy
     uint64_t *wres = hready + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wres + 1);
 
@@ -157,8 +160,10 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], kTfEpi);
         }
-        mbar_init(hfull, 1);
-        mbar_init(hempty, kTfEpi);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&hfull[s], 1);
+            mbar_init(&hempty[s], kTfEpi);
+        }
         mbar_init(hready, kTfEpi);
         mbar_init(wres, 1);
         fence_barrier_init();
@@ -173,15 +178,15 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t kColH = 128;                  // TMEM: U accumulators at columns [0,64) [64,128), Hacc at [128,192)
+    constexpr uint32_t kColH = 128;                  // TMEM: U accumulators at columns [0,64) [64,128), Hacc at [128,192) [192,256)
 
     // This CTA's items: cta_in_box, + ctas_per_box, ...; step s = (item s/17, joint s%17).
     const int nitems = cta_in_box < prm.nq_items ? (prm.nq_items - cta_in_box + ctas_per_box - 1) / ctas_per_box : 0;
     const int nsteps = nitems * 17;
 
     if (warp == 0) {
-        // ===== producer: weights once, then per step the C/64 Y-window boxes (and, projection blocks, the cin/64
-        // input boxes of the PREVIOUS step), in the order the MMA issuer consumes them: A(0) [A(1) B(0)] [A(2) B(1)] ...
+        // ===== producer: weights once, then the C/64 Y-window boxes two steps ahead and the residual-input boxes of
+        // this step, in the order the MMA issuer consumes them: A(0) A(1) [B(0) A(2)] [B(1) A(3)] ...
         if (elect_one()) {
             mbar_expect_tx(wres, prm.w1_bytes + prm.w2_bytes + prm.wr_bytes + 4096u);
             tma_load_2d(smem + prm.bias_off + 4096, &maps.bt1, wres, 0, q * 64);
@@ -216,14 +221,14 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             }
         };
         if (nsteps > 0) load_boxes(0, 0);
+        if (nsteps > 1) load_boxes(1, 0);
         for (int st = 0; st < nsteps; ++st) {
             load_boxes(st, 1);
-            if (st + 1 < nsteps) load_boxes(st + 1, 0);
+            if (st + 2 < nsteps) load_boxes(st + 2, 0);
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: A(n) = the 1x1 into Hacc, B(n) = projection chunks + 3 taps x branches-in-box into one
-        // 64-column U accumulator.  Order A(0) [B(0) A(1)] [B(1) A(2)] ...: the next step's 1x1 is in the tensor
-        // pipe while the epilogue warps drain this step. =====
+        // ===== MMA issuer: A(n) = bias + the 1x1 into Hacc[n & 1], B(n) = bias + residual chunks + 3 taps x
+        // branches-in-box into one 64-column U accumulator.  Order A(0) A(1) [B(0) A(2)] [B(1) A(3)] ... =====
         int slot = 0;
         uint32_t phase = 0;
         constexpr uint32_t wrow_bytes = (uint32_t)CRM * 2;
@@ -246,30 +251,35 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             dbv[i] = make_kmajor_desc(smem_u32(smem + prm.w2_off + (size_t)i * (CRM * CRM * 2)), wrow_bytes);
         }
         const uint64_t dh = make_kmajor_desc(smem_u32(smem + prm.hbox_off), 128);
+        const uint64_t d_ring = make_kmajor_desc(smem_u32(smem), 128);                  // ring slot 0; + slot * (16384 >> 4)
+        const uint64_t d_w1 = make_kmajor_desc(smem_u32(smem + prm.w1_off), 128);       // + kb * (8192 >> 4)
+        const uint64_t d_wr = make_kmajor_desc(smem_u32(smem + prm.wr_off), 128);
         const uint64_t d_ones = make_kmajor_desc(smem_u32(smem + prm.bias_off), 32);
         const uint64_t d_b1 = make_kmajor_desc(smem_u32(smem + prm.bias_off + 4096), 32);
         const uint64_t d_b2 = make_kmajor_desc(smem_u32(smem + prm.bias_off + 6144), 32);
-        const uint32_t th = tmem_base + kColH;
         mbar_wait(wres, 0);
         auto issue_a = [&](uint32_t n) {
             if (lane == 0) TF_TRACE(2, n, 0);
-            mbar_wait(hempty, (n & 1u) ^ 1u);
+            const uint32_t hb = n & 1u;
+            const uint32_t th = tmem_base + kColH + hb * 64u;
+            mbar_wait(&hempty[hb], ((n >> 1) & 1u) ^ 1u);
             if (lane == 0) TF_TRACE(2, n, 1);
             tc_fence_after();
             if (elect_one()) umma_bf16(th, d_ones, d_b1, idesc_64, 0u);     // Hacc = b1
             for (int kb = 0; kb < prm.nky; ++kb) {
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
-                const uint64_t da = make_kmajor_desc(smem_u32(smem + (size_t)slot * kBoxBytes), 128);
-                const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.w1_off + (size_t)kb * 8192), 128);
+                const uint64_t da = d_ring + (uint64_t)((uint32_t)slot * (kBoxBytes >> 4));
+                const uint64_t db = d_w1 + (uint64_t)((uint32_t)kb * (8192u >> 4));
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (elect_one()) umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
-                if (elect_one()) umma_commit(&empty[slot]);
+                    for (int k = 0; k < 4; ++k) umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
+                    umma_commit(&empty[slot]);
+                }
                 __syncwarp();
                 if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
-            if (elect_one()) umma_commit(hfull);
+            if (elect_one()) umma_commit(&hfull[hb]);
             __syncwarp();
             if (lane == 0) TF_TRACE(2, n, 2);
         };
@@ -284,12 +294,13 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             for (int kx = 0; kx < prm.nkx; ++kx) {
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
-                const uint64_t da = make_kmajor_desc(smem_u32(smem + (size_t)slot * kBoxBytes), 128);
-                const uint64_t db = make_kmajor_desc(smem_u32(smem + prm.wr_off + (size_t)kx * 8192), 128);
+                const uint64_t da = d_ring + (uint64_t)((uint32_t)slot * (kBoxBytes >> 4));
+                const uint64_t db = d_wr + (uint64_t)((uint32_t)kx * (8192u >> 4));
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (elect_one()) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
-                if (elect_one()) umma_commit(&empty[slot]);
+                    for (int k = 0; k < 4; ++k) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
+                    umma_commit(&empty[slot]);
+                }
                 __syncwarp();
                 if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
@@ -311,9 +322,10 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (lane == 0) TF_TRACE(2, n, 7);
         };
         if (nsteps > 0) issue_a(0u);
+        if (nsteps > 1) issue_a(1u);
         for (int st = 0; st < nsteps; ++st) {
             issue_b((uint32_t)st);
-            if (st + 1 < nsteps) issue_a((uint32_t)st + 1u);
+            if (st + 2 < nsteps) issue_a((uint32_t)st + 2u);
         }
     } else {
         // ===== epilogue warps: per iteration convert(n) and epilogue(n-1).  Warp w owns TMEM lanes (rows)
@@ -333,7 +345,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         const uint32_t row_off1 = (uint32_t)r * 128u + (uint32_t)(((cq * 2 + 1) ^ (r & 7)) << 4);
         const uint32_t hb0 = smem_u32(smem + prm.hbox_off) + row_off0, hb1 = smem_u32(smem + prm.hbox_off) + row_off1;
         const uint32_t out_base = smem_u32(smem + prm.out_off);
-        const uint32_t a_hfull = smem_u32(hfull), a_hempty = smem_u32(hempty), a_hready = smem_u32(hready);
+        const uint32_t a_hfull = smem_u32(hfull), a_hempty = smem_u32(hempty), a_hready = smem_u32(hready);   // [2], [2], [1]
         const uint32_t a_tfull = smem_u32(tfull), a_tempty = smem_u32(tempty);
         unsigned char *sout = smem + prm.out_off;
         float *scr = reinterpret_cast<float *>(smem + prm.scr_off);    // [2][16 parts][64]
@@ -384,15 +396,15 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 // U accumulator of step n-1 complete => its MMAs have also finished reading Hbox
                 mbar_wait_u32(a_tfull + buf * 8u, (m >> 1) & 1u);
             }
-            if (do_cv) mbar_wait_u32(a_hfull, n & 1u);
+            if (do_cv) mbar_wait_u32(a_hfull + (n & 1u) * 8u, (n >> 1) & 1u);
             if (trole >= 0) TF_TRACE(trole, n, 2);
             tc_fence_after();
-            if (do_cv) tmem_ld16(t_h, acch);
+            if (do_cv) tmem_ld16(t_h + (n & 1u) * 64u, acch);
             if (rows_live) tmem_ld16(t_u + buf * 64u, accu);
             tmem_ld_wait();
             if (trole >= 0) TF_TRACE(trole, n, 3);
             tc_fence_before();
-            if (do_cv) mbar_arrive_u32(a_hempty);
+            if (do_cv) mbar_arrive_u32(a_hempty + (n & 1u) * 8u);
             if (do_ep) mbar_arrive_u32(a_tempty + buf * 8u);
             if (do_cv) {
                 // ---- convert(n): Hacc (b1 included) -> ReLU + bf16 in one conversion, zero outside [0,T) -> K-major Hbox
