@@ -112,6 +112,14 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory slot, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // CR = channels per branch (8 / 16 / 32 / 64): compile-time so the tap loop of the MMA issuer is straight-line
 // code (12 tcgen05.mma per step with loop-invariant operand offsets; 24 for CR = 8).  A bf16 MMA needs
 // K = 16 and N % 16 == 0, so 8-channel branches (the R = 8 stress config at C = 64) run as 16-wide MMAs over
@@ -220,9 +228,29 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
         };
+        // The ring holds 5-8 boxes (80-128 KB in flight) and the Y windows come from DRAM (the graph-conv kernel wrote
+        // 170-670 MB just before): measured, the C = 256 launches slow down 17 % with 4 slots instead of 6, i.e. they
+        // are bound by bytes in flight x latency.  When the ring cannot hold one step's boxes (the 128 -> 256 block: 6
+        // boxes, 5 slots) each CTA asks L2 for ITS share of the boxes kPfAhead steps ahead (Y box q of the window - the
+        // nboxes CTAs of an item cover the window between them - and its residual box), so the ring's loads find them
+        // in L2: 0.61 -> 0.56 ms on that launch.  With a deeper ring the prefetches only cost (+3 %): off.
+        auto prefetch_boxes = [&](int st) {
+            const int item = cta_in_box + (st / 17) * ctas_per_box, v = st % 17;
+            const int b = item / prm.ttiles, t0 = (item % prm.ttiles) * nout;
+            if (elect_one()) {
+                tma_prefetch_4d(&maps.y_win, q * 64, t0 - prm.dmax, v, b);
+                if (prm.res_q) tma_prefetch_4d(&maps.xg, q * 64, v, t0, b);
+                else if (q < prm.nkx) tma_prefetch_4d(&maps.xg, q * 64, v, t0, b);
+            }
+            __syncwarp();
+        };
+        constexpr int kPfAhead = 6;
+        const bool pf = prm.nky + prm.nkx >= SLOTS;
+        for (int st = 0; pf && st < kPfAhead && st < nsteps; ++st) prefetch_boxes(st);
         if (nsteps > 0) load_boxes(0, 0);
         if (nsteps > 1) load_boxes(1, 0);
         for (int st = 0; st < nsteps; ++st) {
+            if (pf && st + kPfAhead < nsteps) prefetch_boxes(st + kPfAhead);
             load_boxes(st, 1);
             if (st + 2 < nsteps) load_boxes(st + 2, 0);
         }
