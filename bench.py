@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_traffic.json")
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_final_traffic.json")
 METRIC = "swing clips/sec (T=300,V=17)"
 UNIT = "clips/s"
 T_FRAMES = 300
@@ -541,7 +541,7 @@ def main():
                                                         for bk, bv in v.get("blocks", {}).items()}}
         top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
         # ncu dram bytes per launch of that kernel: from the ncu --set full capture of THIS code state
-        # (profiles/r2_traffic.json, written by tools/ncu_summary.py --traffic from the capture of tools/ncu_run.sh)
+        # (profiles/r2_final_traffic.json, written by tools/ncu_summary.py --traffic from the capture of tools/ncu_run.sh)
         traffic = None
         if os.path.exists(TRAFFIC_JSON) and B == BATCH:
             traffic = json.load(open(TRAFFIC_JSON)).get(top, {}).get("bytes_per_launch")
@@ -550,7 +550,7 @@ def main():
         t_s = tv["ms"] * 1e-3
         floor_tensor = tv["flops"] / (peaks["tf_sust"] * 1e12)
         floor_hbm = tv["bytes"] / (peaks["hbm"] * 1e9)
-        common = {"kernel": top, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r2_traffic.json)",
+        common = {"kernel": top, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r2_final_traffic.json)",
                   "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
                   "algorithmic_flops_per_launch": tv["flops"] / tv["launches"],
                   "frac_of_tensor_roof": floor_tensor / t_s, "frac_of_hbm_roof": floor_hbm / t_s}

@@ -11,6 +11,6 @@ tail -2 gpurun_out/${TAG}_ncu1.log | cut -c1-200
 python tools/prof_seg.py > gpurun_out/${TAG}_prof_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -s 25 -c 25 -o gpurun_out/${TAG}_full python tools/prof_seg.py > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu2.log | cut -c1-200
-ncu --set full --clock-control none --import-source on -k regex:"dtw_pipeline" -s 1 -c 1 -o gpurun_out/${TAG}_dtw $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"dtw_ws" -s 1 -c 1 -o gpurun_out/${TAG}_dtw $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu3.log | cut -c1-200
 ls -la gpurun_out | tail -8

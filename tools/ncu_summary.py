@@ -61,7 +61,7 @@ def rep_table(path):
 
 # ncu kernel name -> the name bench.py's profiler uses for it
 BENCH_NAMES = {"gcn_fused_kernel": "bf16_gemm_gcn", "tcn_fused_kernel": "bf16_tconv", "head_stream_kernel": "head",
-               "front_mma_kernel": "bf16_front", "dtw_pipeline2_kernel": "dtw_wavefront", "stj_tc_kernel": "stj_gate",
+               "front_mma_kernel": "bf16_front", "dtw_ws_kernel": "dtw_wavefront", "dtw_pipeline2_kernel": "dtw_wavefront", "stj_tc_kernel": "stj_gate",
                "se_kernel": "se_gate", "dtw_backtrack_kernel": "dtw_backtrack"}
 
 
