@@ -37,4 +37,4 @@ for blk in range(1, 6):
         print(f"          conv d1_full{rel(t[2, tile, :nq])}")
         print(f"          conv xa_empt{rel(t[2, tile, 16:16 + nq])}")
         print(f"          conv publish{rel(t[2, tile, 32:32 + nq])}")
-        print(f"          epi  {rel(t[4, tile, :2])}")
+        print(f"          epi  woke, stored, drained {rel(t[4, tile, :3])}")
