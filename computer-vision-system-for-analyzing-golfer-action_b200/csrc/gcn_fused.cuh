@@ -31,8 +31,16 @@
 //                          C = 256 there is room for ONE accumulator in tensor memory, so the drain time is
 //                          what the next tile's MMA2 waits for: ~400 cycles this way, ~6000 when each box was
 //                          staged before the next was read.
-// Measured before the split (4 warps per role, 64 columns per thread): convert 800-1100 cycles per
-// chunk against 896 of tensor work at C=256, gate 3000 cycles per box, epilogue 1700 per box.
+// WHAT BOUNDS IT: the shared-memory data pipe (128 B per clock and SM), not the tensor pipe and not HBM.  ncu on the
+// C = 256 launch of the round-2 mid state: l1tex__data_pipe_lsu_wavefronts_mem_shared 68 % of peak + l1tex__data_pipe_tc_
+// wavefronts_mem_shared (UMMA operand reads) 36 % = 104 %.  Per 119-row tile at Cin = C = 256, in 128-byte wavefronts:
+//   UMMA reads   MMA2 A (XA chunk) 12 x 128 + B (weights) 12 x 256 = 4.6 k,  MMA1 B (the X box, once per partition) 1.5 k
+//   TMA writes   weights 3.1 k, X boxes + gate slices 0.75 k;   TMA store reads  Xg 0.5 k, Y 0.5 k
+//   LDS / STS    convert 1.5 k, gate 1.6 k (5.1 k before the remap below), epilogue 0.5 k
+// = ~14.5 k against a measured tile period of ~14 k cycles (16.5 k before).  With M = 128 and both operands in shared
+// memory an N = 256 MMA alone reads 96 B per clock; halving the weight traffic needs cta_group::2, which the TS-form
+// MMA1 (a different B operand per CTA) does not fit.  The smaller widths run at the same wall: C = 64: ~2.9 k wavefronts
+// per tile, period 3.3 k cycles.
 // The input tile moves through a RING of 64-channel boxes (X box + its gT / gV slices, all three
 // brought by TMA); a box is released after its three MMA1s (chunk order: box-major, partition
 // minor), so the next tile's boxes load and get gated while this tile is still in the MMAs.
@@ -67,7 +75,8 @@ struct Params {
     const float *gT;      // [B,T,Cin]   (maps carry the data; non-null = gating on)
     const float *gV;      // [B,17,Cin]
     const float *A;       // [3,17,17] fp32
-    const float *bias;    // [C]
+    float biasv[256];     // [C] by value: the epilogue warps read it through the constant bank with warp-uniform indices
+                          // (16 shared-memory loads per thread and tile less in a kernel bound by the shared-memory pipe)
     __nv_bfloat16 *dbg_xa;       // optional [ntiles*128, 3*Cin] dump of the converted XA chunks
     unsigned long long *trace;   // optional clock64 trace of CTA 0 (tools/trace_gcn.py)
 };
@@ -143,6 +152,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return d;
 }
 
+// NBOX = C / 64 as a template parameter: the epilogue's per-box loops are straight-line code and the packed results stay in
+// registers (with C as a run-time value the compiler indexed them in local memory: stores and loads through the same pipe
+// the kernel is bound by).
+template <int NBOX>
 __global__ void __launch_bounds__(kThreadsGcn, 1)
 gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXg,
                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapY,
@@ -168,7 +181,8 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_full + 10);
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-    const int Cin = prm.Cin, C = prm.C;
+    const int Cin = prm.Cin;
+    constexpr int C = NBOX * 64;
     const int nbc = Cin / 64;       // 64-channel boxes of the input tile
     const int nq = 3 * nbc;         // XA chunks (= K chunks of the channel mix) per tile
 
@@ -206,8 +220,6 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    float *sbias = reinterpret_cast<float *>(smem + lay.bar_off + 512);
-    for (int k = threadIdx.x; k < C; k += kThreadsGcn) sbias[k] = prm.bias[k];
     // ---- one-time: block-diagonal adjacency Abig_p = I_7 (x) A_p into tensor memory --------
     if (warp >= 4 && warp < 8) {
         const int r = (warp - 4) * 32 + lane;          // output row (w of frame f)
@@ -398,22 +410,23 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const bool leader = (gt_id == 0);
         int slot = 0, prev_slot = -1, tcount = 0;
         uint32_t ph = 0;
+        // (clip, tile in clip) advance by gridDim.x tiles without a division per tile
+        const int step_b = (int)gridDim.x / prm.mtiles, step_m = (int)gridDim.x % prm.mtiles;
+        int b = (int)blockIdx.x / prm.mtiles, mt = (int)blockIdx.x % prm.mtiles;
         for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++tcount) {
-            const int tl = tile;
-            const int b = tl / prm.mtiles;
-            const int row0 = (tl % prm.mtiles) * kRowsPerTile;
+            const int row0 = mt * kRowsPerTile;
             for (int cb = 0; cb < nbc; ++cb) {
                 unsigned char *sl = smem + lay.x_off + (size_t)slot * kSlotBytes;
                 mbar_wait(&x_full[slot], ph);
                 if (leader) GCN_TRACE(3, tcount, cb);
                 if (prm.gT) {
-                    // The kernel is bound by SHARED-MEMORY bandwidth at C = 256 (per tile ~2 MB of wavefronts: MMA operand
-                    // reads, TMA writes, convert / epilogue stores and this role), so the mapping minimises wavefronts:
-                    // thread = (4-channel group g, joints j, j + 8 [, 16]) for all 7 frames.  A half-warp reads one
-                    // whole 128-byte row (1 wavefront), a quarter-warp reads 128 contiguous bytes of a gate row (no
-                    // bank conflict), gV stays in registers over the frames and gT over the joints: ~400 wavefronts
-                    // per box.  The earlier mapping (16-byte x vectors, four 16-byte gate loads per vector at a
-                    // 32-byte lane stride = 2-way conflicts) needed ~1300 and ncu counted 44 M load conflicts per launch.
+                    // The kernel is bound by the SHARED-MEMORY data pipe (header comment), so the mapping minimises
+                    // wavefronts: thread = (4-channel group g, joints j, j + 8) for all 7 frames, plus one row of joint
+                    // 16.  A half-warp reads one whole 128-byte row (1 wavefront), a quarter-warp reads 128 contiguous
+                    // bytes of a gate row (no bank conflict), gV stays in registers over the frames and gT over the two
+                    // joints: ~400 wavefronts per box.  The earlier mapping (16-byte x vectors, four 16-byte gate
+                    // loads per vector at a 32-byte lane stride = 2-way conflicts) needed ~1300, and ncu counted 44 M
+                    // shared-load bank conflicts per C = 256 launch.
                     const float4 *sgt = reinterpret_cast<const float4 *>(sl + kGtOff);   // [8 frames][16 groups]
                     const float4 *sgv = reinterpret_cast<const float4 *>(sl + kGvOff);   // [17 joints][16 groups]
                     const int g = gt_id & 15, j = gt_id >> 4;
@@ -429,27 +442,36 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         const float2 c2 = fmul2(fmul2(__bfloat1622float2(xp[1]), make_float2(t.z, t.w)), make_float2(v.z, v.w));
                         *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(c2.x, c2.y));
                     };
-                    // joint 16: one row per thread, thread (g, j) takes frame j
-                    if (j < fv) {
+                    // A rolled loop over the frames (one frame = the rows of joints j and j + 8), software-pipelined by
+                    // hand: the next frame's three loads are issued before this frame's arithmetic and stores (the
+                    // compiler cannot move a load above a store that may alias).  A box still takes ~2000 cycles in
+                    // these warps, ~50 cycles per LDS / STS whatever the form of the loop (row by row, all loads first,
+                    // rolled: tools/trace_gcn.py): the instructions queue for a data pipe that is full.
+                    const float4 gv0 = sgv[j * 16 + g], gv1 = sgv[(j + 8) * 16 + g];
+                    if (j < fv) {       // joint 16: thread (g, j < 7) takes the row of frame j
                         const int r = j * 17 + 16;
                         unsigned char *p = colp + (size_t)r * 128 + (((g >> 1) ^ (r & 7)) << 4);
                         gate_row(p, *reinterpret_cast<const uint2 *>(p), sgt[j * 16 + g], sgv[16 * 16 + g]);
                     }
-                    // joints j and j + 8 over the frames: gV in registers, gT loaded once per frame for both rows
-                    const float4 gv0 = sgv[j * 16 + g], gv1 = sgv[(j + 8) * 16 + g];
-#pragma unroll
-                    for (int f = 0; f < kFramesPerTile; ++f) {
-                        if (f < fv) {                                       // uniform over the CTA
-                            const float4 t = sgt[f * 16 + g];
-                            const int rb = f * 17 + j;                      // rows rb and rb + 8 share r & 7
-                            unsigned char *p = colp + (size_t)rb * 128 + (((g >> 1) ^ (rb & 7)) << 4);
-                            const uint2 x0 = *reinterpret_cast<const uint2 *>(p);
-                            const uint2 x1 = *reinterpret_cast<const uint2 *>(p + 1024);
-                            gate_row(p, x0, t, gv0);
-                            gate_row(p + 1024, x1, t, gv1);
-                        }
+                    const uint32_t gsw = (uint32_t)(g >> 1);
+                    unsigned char *p = colp + (size_t)j * 128 + ((gsw ^ (uint32_t)(j & 7)) << 4);   // row j of frame 0
+                    float4 t = sgt[g];
+                    uint2 x0 = *reinterpret_cast<const uint2 *>(p), x1 = *reinterpret_cast<const uint2 *>(p + 1024);
+#pragma unroll 1
+                    for (int f = 0; f < fv; ++f) {
+                        // prefetch frame f + 1 (the last pass re-reads frame 6's gT row and an in-box row: unused)
+                        const int fn = f + 1 < kFramesPerTile ? f + 1 : f;
+                        unsigned char *rown = colp + (size_t)(fn * 17 + j) * 128;
+                        unsigned char *pn = rown + ((gsw ^ ((uint32_t)(fn * 17 + j) & 7)) << 4);
+                        const float4 tn = sgt[fn * 16 + g];
+                        const uint2 x0n = *reinterpret_cast<const uint2 *>(pn), x1n = *reinterpret_cast<const uint2 *>(pn + 1024);
+                        gate_row(p, x0, t, gv0);
+                        gate_row(p + 1024, x1, t, gv1);
+                        p = pn; t = tn; x0 = x0n; x1 = x1n;
                     }
+                    if (leader) GCN_TRACE(3, tcount, 32 + cb);
                     fence_proxy_async_smem();
+                    if (leader) GCN_TRACE(3, tcount, 36 + cb);
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (leader) {
@@ -458,12 +480,14 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                     if (prm.store_xg) {
                         tma_store_3d(&mapXg, sl, cb * 64, row0, b);
                         tma_store_commit();
+                        GCN_TRACE(3, tcount, 48 + cb);
                         // the PREVIOUS box's store has been in flight for a whole box period: drain it now
                         // and release its slot (deferred wait keeps the gate pipeline moving)
                         if (prev_slot >= 0) {
                             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             mbar_arrive(&x_empty[prev_slot]);
                         }
+                        GCN_TRACE(3, tcount, 52 + cb);
                         prev_slot = slot;
                     } else {
                         mbar_arrive(&x_empty[slot]);     // nothing reads the box but the MMA1s
@@ -471,6 +495,9 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 }
                 if (++slot == XS) { slot = 0; ph ^= 1; }
             }
+            b += step_b;
+            mt += step_m;
+            if (mt >= prm.mtiles) { mt -= prm.mtiles; ++b; }
         }
         if (leader) {
             tma_store_wait_read0();
@@ -493,30 +520,25 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mbar_wait(&acc_full[as], aph);
             if (leader) GCN_TRACE(4, tcount, 0);
             tc_fence_after();
-            uint32_t pk[4][8];                       // up to 4 boxes (C <= 256) x 16 bf16
+            uint32_t pk[NBOX][8];                    // NBOX boxes x 16 bf16
+            // cq comes from the warp index, so the bias index is warp-uniform: constant-bank operands, no LDS
 #pragma unroll
-            for (int qb = 0; qb < 4; ++qb) {
-                if (qb < C / 64) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64 + cq * 16), v);
-                    tmem_ld_wait();
-                    const float *bq = sbias + qb * 64 + cq * 16;
+            for (int qb = 0; qb < NBOX; ++qb) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + as * (uint32_t)C + (uint32_t)(qb * 64 + cq * 16), v);
+                tmem_ld_wait();
+                const float *bq = prm.biasv + qb * 64 + cq * 16;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(bq + e * 4);
-                        pk[qb][2 * e] = pack_bf16(fmaxf(__uint_as_float(v[4 * e + 0]) + bb.x, 0.f),
-                                                  fmaxf(__uint_as_float(v[4 * e + 1]) + bb.y, 0.f));
-                        pk[qb][2 * e + 1] = pack_bf16(fmaxf(__uint_as_float(v[4 * e + 2]) + bb.z, 0.f),
-                                                      fmaxf(__uint_as_float(v[4 * e + 3]) + bb.w, 0.f));
-                    }
-                }
+                for (int e = 0; e < 8; ++e)
+                    pk[qb][e] = pack_bf16(fmaxf(__uint_as_float(v[2 * e]) + bq[2 * e], 0.f),
+                                          fmaxf(__uint_as_float(v[2 * e + 1]) + bq[2 * e + 1], 0.f));
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[as]);             // accumulator fully read: the next tile's MMA2 may start
             if (leader) GCN_TRACE(4, tcount, 2);
 #pragma unroll
-            for (int qb = 0; qb < 4; ++qb) {
-                if (qb < C / 64) {
+            for (int qb = 0; qb < NBOX; ++qb) {
+                {
                     const uint32_t es = ecnt % (uint32_t)ES;
                     // staging slot reuse: the store issued ES boxes ago must have finished reading it
                     if (leader && ecnt >= (uint32_t)ES) {
@@ -590,12 +612,16 @@ inline int launch(Ctx *ctx, int kid, LaunchGcn &L, cudaStream_t st) {
     const Smem lay = smem_layout(L.prm.C, L.prm.xslots, L.prm.wstages, L.prm.eslots);
     int grid = L.prm.ntiles < ctx->sm_count ? L.prm.ntiles : ctx->sm_count;
     if (grid < 1) return GS_OK;
-    int rc = ensure_dyn_smem(ctx, (const void *)gcn_fused_kernel, lay.total);
+    auto kern = L.prm.C == 64 ? gcn_fused_kernel<1> : (L.prm.C == 128 ? gcn_fused_kernel<2> : gcn_fused_kernel<4>);
+    if (L.prm.C != 64 && L.prm.C != 128 && L.prm.C != 256) {
+        set_error("gcn_fused: C must be 64, 128 or 256 (C=%d)", L.prm.C);
+        return GS_ERR_UNSUPPORTED;
+    }
+    int rc = ensure_dyn_smem(ctx, (const void *)kern, lay.total);
     if (rc != GS_OK) return rc;
     {
         LaunchScope ls(ctx, kid, st, L.flops, L.bytes);
-        gcn_fused_kernel<<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT, L.mapGV,
-                                                               L.prm);
+        kern<<<grid, kThreadsGcn, lay.total, st>>>(L.mapX, L.mapXg, L.mapW, L.mapY, L.mapGT, L.mapGV, L.prm);
     }
     GS_KERNEL_CHECK();
     return GS_OK;

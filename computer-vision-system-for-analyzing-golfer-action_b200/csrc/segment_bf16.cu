@@ -29,6 +29,7 @@ struct Bf16Path {
     std::vector<__nv_bfloat16 *> WgT, W1T, W2p, WrT;   // device bf16 weights, K contiguous
     std::vector<__nv_bfloat16 *> Bt1, Bt2;              // bias tiles [C][16] of the temporal kernel: b1; b2 (+ br)
     std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in fp16 fragment order (stj_tc_kernel)
+    std::vector<std::vector<float>> bgHost;             // host copies of the GCN biases: they travel as kernel parameters (gcn_fused.cuh)
     float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
     __nv_bfloat16 *ident64 = nullptr;                   // 64x64 identity: "projection" weights of the identity residual (tcn_fused.cuh)
     std::vector<BlockMaps> maps;
@@ -342,6 +343,8 @@ int bf16_path_create(Ctx *ctx) {
             }
             if ((rc = upload_bf16(ctx, h, &bp->W2p[i]))) return rc;
         }
+        bp->bgHost.resize(nb);
+        bp->bgHost[i].assign(host(b.bg), host(b.bg) + C);
         std::vector<float> bias(host(b.b2), host(b.b2) + C);
         if (i > 0 && b.has_res) {   // WrT [C][cin]; its bias joins b2
             const float *W = host(b.Wr);
@@ -481,7 +484,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             q.gV = ctx->gV;
             q.store_xg = 1;
             q.A = b.A;
-            q.bias = b.bg;
+            memcpy(q.biasv, bp->bgHost[i].data(), (size_t)C * sizeof(float));
             q.dbg_xa = bp->debug_xa ? XA : nullptr;      // sized for whole tiles in alloc_workspace when the switch is on
             q.trace = bp->trace ? bp->trace + (size_t)i * 5 * gcn::kTraceTiles * gcn::kTraceEv : nullptr;
             L.flops = 2.0 * rows * (V17 * 3.0 * cin + 3.0 * cin * C);

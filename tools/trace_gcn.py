@@ -31,6 +31,7 @@ for blk in range(1, 6):
         rel = lambda a: [int(v - t0) if v > 0 else -1 for v in a]
         print(f" tile {tile}: prod box-issue {rel(t[0, tile, :cin // 64])}")
         print(f"          gate x_full {rel(t[3, tile, :cin // 64])} x_ready {rel(t[3, tile, 16:16 + cin // 64])}")
+        print(f"          gate computed {rel(t[3, tile, 32:32 + cin // 64])} fenced {rel(t[3, tile, 36:36 + cin // 64])} store issued {rel(t[3, tile, 48:48 + cin // 64])} prev drained {rel(t[3, tile, 52:52 + cin // 64])}")
         print(f"          mma  MMA1   {rel(t[1, tile, :nq])}")
         print(f"          mma  xa_full{rel(t[1, tile, 16:16 + nq])}")
         print(f"          mma  w_full {rel(t[1, tile, 32:32 + nq])}")
