@@ -125,6 +125,11 @@ struct Ctx {
 
     cudaStream_t own_stream[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
+    // gs_segment_host, bf16 path: the input arrives in chunks on the copy stream; only block 0's input kernel is
+    // launched per chunk (behind ev_front[k]), every later kernel runs once on the whole batch
+    static constexpr int kFrontChunks = 4;
+    cudaEvent_t ev_front[kFrontChunks] = {nullptr, nullptr, nullptr, nullptr};
+    int front_nchunks = 0, front_b0[kFrontChunks] = {0, 0, 0, 0}, front_nb[kFrontChunks] = {0, 0, 0, 0};
     bool ev_valid = false;
     // Every entry point shares this context's workspace, whatever stream it runs on: each call records
     // `ev_last` behind its work and the next call's stream(s) wait for it first, so sequential calls from

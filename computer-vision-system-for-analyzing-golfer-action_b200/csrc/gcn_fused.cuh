@@ -183,6 +183,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int Cin = prm.Cin;
     constexpr int C = NBOX * 64;
+    constexpr bool kSplit = (NBOX == 4);   // one accumulator, released in two halves (plan_smem: nacc = 1 exactly when C = 256)
     const int nbc = Cin / 64;       // 64-channel boxes of the input tile
     const int nq = 3 * nbc;         // XA chunks (= K chunks of the channel mix) per tile
 
@@ -333,6 +334,7 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     } else if (warp == 2) {
         // ===== MMA2 issuer: acc (+)= XA chunk . WgT chunk^T =====
         const uint32_t idesc2 = make_idesc_bf16((uint32_t)C);
+        const uint32_t idesc_half = make_idesc_bf16(128u);
         uint32_t xa_cnt = 0;        // running count of XA chunks consumed
         uint32_t acc_cnt = 0;       // running count of tiles (accumulator uses)
         int wstage = 0, tcount = 0;
@@ -342,13 +344,33 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const uint32_t td = tmem_base + as * (uint32_t)C;
             for (int j = 0; j < nq; ++j) {
                 const uint32_t slot = xa_cnt & 1, ph = (xa_cnt >> 1) & 1;
-                if (j == 0) mbar_wait(&acc_empty[as], aph ^ 1);   // epilogue has drained this accumulator
+                if (j == 0) mbar_wait(&acc_empty[as], aph ^ 1);   // epilogue has drained this accumulator (its low half: kSplit)
                 mbar_wait(&xa_full[slot], ph);
                 mbar_wait(&w_full[wstage], wph);
                 tc_fence_after();
                 const uint64_t da = make_kmajor_desc(smem_u32(smem + lay.xa_off + slot * 16384u), 128);
                 const uint64_t db = make_kmajor_desc(smem_u32(smem + lay.w_off + (size_t)wstage * lay.w_stage_bytes), 128);
-                if (elect_one()) {
+                if (kSplit && j == 0) {
+                    // one accumulator (C = 256): the tile's first chunk is issued as two N = 128 halves, the low one as soon
+                    // as the epilogue has read columns [0,128) of the previous tile: the tensor pipe restarts half a drain
+                    // (~700 cycles of ~1500: the TMEM read-out of 128 KB) earlier
+                    if (elect_one()) {
+                        GCN_TRACE(1, tcount, 16 + j);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_half, (uint32_t)(k > 0));
+                    }
+                    __syncwarp();
+                    mbar_wait(&acc_empty[1], aph ^ 1);            // high half drained
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(td + 128u, da + (uint64_t)(2 * k), db + (uint64_t)(1024 + 2 * k), idesc_half, (uint32_t)(k > 0));
+                        umma_commit(&xa_empty[slot]);
+                        umma_commit(&w_empty[wstage]);
+                    }
+                } else if (elect_one()) {
                     GCN_TRACE(1, tcount, 16 + j);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
@@ -532,9 +554,13 @@ gcn_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 for (int e = 0; e < 8; ++e)
                     pk[qb][e] = pack_bf16(fmaxf(__uint_as_float(v[2 * e]) + bq[2 * e], 0.f),
                                           fmaxf(__uint_as_float(v[2 * e + 1]) + bq[2 * e + 1], 0.f));
+                if (kSplit && qb == 1) {             // columns [0,128) read: the low half of the next tile's first chunk may start
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[0]);
+                }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[as]);             // accumulator fully read: the next tile's MMA2 may start
+            mbar_arrive(&acc_empty[kSplit ? 1 : as]);   // accumulator fully read: the next tile's MMA2 may start
             if (leader) GCN_TRACE(4, tcount, 2);
 #pragma unroll
             for (int qb = 0; qb < NBOX; ++qb) {

@@ -457,13 +457,23 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         const bool proj = (i > 0 && b.has_res);
         if (i == 0) {
             const size_t smem = ((size_t)3 * V17 * V17 + 1 + (size_t)kFrontFrames * V17 * (cin + kFrontLd)) * sizeof(float);
-            {
-                LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * rows * (V17 * 3 * cin + 4 * cin * C),
-                               rows * (cin * 4 + 4.0 * C));
-                front_mma_kernel<3><<<cdiv(nframes, kFrontFrames), 256, smem, st>>>(
-                    skel, ctx->in_scale, ctx->in_shift, b.A, bp->frontB, C, T, nframes, Y, R0);
+            // one launch, or one per input chunk of gs_segment_host (whole clips: both output layouts are per clip)
+            const int nch = ctx->front_nchunks > 0 ? ctx->front_nchunks : 1;
+            for (int k = 0; k < nch; ++k) {
+                const size_t b0 = ctx->front_nchunks > 0 ? (size_t)ctx->front_b0[k] : 0;
+                const size_t nbk = ctx->front_nchunks > 0 ? (size_t)ctx->front_nb[k] : (size_t)B;
+                if (ctx->front_nchunks > 0) GS_CUDA(cudaStreamWaitEvent(st, ctx->ev_front[k], 0));
+                const size_t nfk = nbk * T;
+                const size_t act0 = b0 * (size_t)T * V17 * C;
+                {
+                    LaunchScope ls(ctx, K_B_FRONT, st, 2.0 * nfk * V17 * (V17 * 3 * cin + 4 * cin * C),
+                                   (double)nfk * V17 * (cin * 4 + 4.0 * C));
+                    front_mma_kernel<3><<<cdiv(nfk, kFrontFrames), 256, smem, st>>>(
+                        skel + b0 * (size_t)T * V17 * cin, ctx->in_scale, ctx->in_shift, b.A, bp->frontB, C, T, nfk,
+                        Y + act0, R0 + act0);
+                }
+                GS_KERNEL_CHECK();
             }
-            GS_KERNEL_CHECK();
         } else {
             gcn::LaunchGcn L{};
             L.mapX = m.f_x_load;
