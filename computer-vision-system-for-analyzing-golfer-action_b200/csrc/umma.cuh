@@ -31,12 +31,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // treat everything after it as potentially divergent, which pushes the MMA / TMA operands into vector
 // registers and costs an R2UR round trip per tcgen05.mma (~200-290 cycles each, measured).
 // mbarrier.try_wait suspends in hardware; a pipeline bug shows up as a hang caught by the caller's timeout.
+// GOLFER_MBAR_HINT (build experiment, e.g. -DGOLFER_MBAR_HINT=", 0x2000"): suspend-time hint in ns on every wait
+#ifndef GOLFER_MBAR_HINT
+#define GOLFER_MBAR_HINT ""
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1" GOLFER_MBAR_HINT ";\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
@@ -50,7 +54,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1" GOLFER_MBAR_HINT ";\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"

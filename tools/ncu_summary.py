@@ -20,6 +20,11 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "l1tex__t_bytes.sum", "lts__t_bytes.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    # the shared-memory data pipe: LSU wavefronts (LDS / STS) and UMMA operand reads; their sum is the utilisation of
+    # the pipe that bounds the two tcgen05 kernels
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 
 
@@ -70,21 +75,33 @@ def traffic_json(reps, out_path, source):
     reads for `roofline.traffic` (regenerated from the capture of THIS code state, never edited by hand)."""
     import json
     agg = collections.OrderedDict()
+    pipes = {}
     for path in reps:
         raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
         ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        pipe = [hdr.index(m) if m in hdr else -1 for m in (
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for r in rows[2:]:
             name = short(r[ki]).split("<")[0].split("::")[-1]
             b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
             agg.setdefault(BENCH_NAMES.get(name, name), []).append(b)
+            pipes.setdefault(BENCH_NAMES.get(name, name), []).append(
+                [float(r[i].replace(",", "")) if i >= 0 and r[i] else 0.0 for i in pipe])
     out = {"source": source}
     total = 0.0
     for k, v in agg.items():
         out[k] = {"bytes_per_launch": sum(v) / len(v), "launches": len(v),
-                  "per_launch_GB": [round(x / 1e9, 3) for x in v]}
+                  "per_launch_GB": [round(x / 1e9, 3) for x in v],
+                  # shared-memory data pipe of each launch: LDS/STS wavefronts + UMMA operand wavefronts, % of peak;
+                  # their sum near 100 = the kernel is bound by that pipe (DESIGN.md section 3)
+                  "smem_pipe_lsu_pct": [round(p[0], 1) for p in pipes[k]],
+                  "smem_pipe_tc_pct": [round(p[1], 1) for p in pipes[k]],
+                  "tensor_pipe_pct": [round(p[2], 1) for p in pipes[k]]}
         total += sum(v)
     out["total_bytes_all_captured_launches"] = total
     json.dump(out, open(out_path, "w"), indent=1)
