@@ -593,9 +593,18 @@ int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, in
         if ((rc = grow(ctx, &ctx->d_al_path, &ctx->al_host_cap[3], (size_t)N * maxL * 2))) return rc;
         if ((rc = grow(ctx, &ctx->d_al_plen, &ctx->al_host_cap[4], (size_t)N))) return rc;
     }
-    // Pairs are independent: chunk so the H2D of chunk k+1 overlaps the DTW of chunk k.
-    const int nchunks = N >= 64 ? 4 : 1;
-    const int per = (N + nchunks - 1) / nchunks;
+    // Pairs are independent: chunk so the H2D of chunk k+1 overlaps the DTW of chunk k.  The call is bound by the
+    // host-to-device copy (334 MB for 4096 pairs of 300 frames: ~6 ms at 55 GB/s against 4 ms of sweep), so what is
+    // left to hide is the tail behind the last copy: the last chunk's sweep and its results.
+    // Chunks are whole rounds of the persistent sweep (a multiple of the SM count: one CTA per SM, pairs one after the
+    // other), about 16 of them: 4096 pairs -> 14 chunks of 296.  Measured (pairs/s end to end): 4 chunks 566 k,
+    // 8 chunks 600 k.
+    int per = N;
+    if (N >= 64) {
+        const int m = (N + 16 * ctx->sm_count - 1) / (16 * ctx->sm_count);
+        per = m * ctx->sm_count;
+        if (N < 4 * per) per = (N + 3) / 4;
+    }
     cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1];
     if ((rc = order_after_previous(ctx, sc))) return rc;
     if ((rc = order_after_previous(ctx, sx))) return rc;
