@@ -815,6 +815,12 @@ def main():
         sl, sb = sseg.segment(skel[:8], return_labels=True)
         label_par["v0_spread"] = label_parity(wants, sl.cpu().numpy(), sb.cpu().numpy(), tol)
         label_par["v0_spread"]["clips_checked"] = 8
+        # this head subtracts each class's mean logit and multiplies by gain / std (6 / ~0.2): the body's rounding error is
+        # amplified by the same factor while max|logit| is not, so the LOGIT bar (1e-2 of max|logit|, held on v0 above and
+        # in tests/) does not apply to it; it exists for the label policy: no mismatch above the margin
+        label_par["v0_spread"]["logits_bar_applies"] = False
+        label_par["v0_spread"]["note"] = ("re-centred, re-scaled head (labels over all 9 classes): label policy only; "
+                                          "the logit tolerance is held on v0")
         sseg.ctx.close()
         if align_obj is not None:
             ar, adt = cpu_align_rate(2048, cores)
