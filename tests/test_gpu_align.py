@@ -105,6 +105,18 @@ def test_cost_only_mode_and_host_entry_point():
     assert np.array_equal(plen_h.numpy(), rl)
 
 
+def test_host_entry_point_many_chunks():
+    """gs_align_host cuts a large batch into chunks of whole sweep rounds (a multiple of the SM count, ~16 chunks):
+    700 pairs = 4 chunks of 148 + 108 on a 148-SM part; results must not depend on the chunking."""
+    a, b = oalign.synth_swings(700, 24, 20, seed=5)
+    rc, rp, rl = align_native.align_batch_c(a, b, 4)
+    cost_h, path_h, plen_h = golfer_b200.host.align_batch(a, b)
+    assert np.array_equal(cost_h.numpy(), rc) and np.array_equal(path_h.numpy(), rp)
+    assert np.array_equal(plen_h.numpy(), rl)
+    cost_d, path_d, plen_d = golfer_b200.host.align_batch(_dev(a), _dev(b))
+    assert np.array_equal(cost_d.cpu().numpy(), rc) and np.array_equal(path_d.cpu().numpy(), rp)
+
+
 def test_public_align_signature_single_pair():
     a, b = oalign.synth_swings(1, 30, 26, seed=2)
     cost, path = golfer_b200.align(_dev(a[0]), _dev(b[0]))
