@@ -530,12 +530,41 @@ def main():
         e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
         barrier()
     e2e_s = min(e2e_runs)
+    sync_call = {"value": world * B * K / e2e_s, "all_repetitions": [world * B * K / t for t in e2e_runs],
+                 "call": "Segmenter.segment(host tensor): one batch at a time, returns when its result is in host memory"}
+    # The same K steps through the PIPELINED public entry point (Segmenter.submit / wait = gs_segment_host_submit /
+    # _wait): every step still copies its own input from pinned host memory and its own result back, inside the timed
+    # region; the copies of one step run under the kernels of its neighbours (two batches in flight).  This is the
+    # call a caller with a stream of batches makes, and the end-to-end number; the one-call-at-a-time rate is beside it.
+    pipe_runs = []
+    if args.precision == "bf16":
+        outs = [torch.empty_like(out_host).pin_memory() for _ in range(2)]
+        for _ in range(W):
+            seg.wait(seg.submit(skel_host, outs[0]))
+        barrier()
+        for _ in range(E2E_REPEATS):
+            t0 = time.perf_counter()
+            prev = None
+            for i in range(K):
+                tk = seg.submit(skel_host, outs[i & 1])      # H2D + kernels + D2H of step i enqueued
+                if prev is not None:
+                    seg.wait(prev)                            # step i-1's result is in host memory
+                prev = tk
+            seg.wait(prev)
+            torch.cuda.synchronize()
+            pipe_runs.append(max_over_ranks(time.perf_counter() - t0))
+            barrier()
+        assert torch.equal(outs[(K - 1) & 1], out_host), "pipelined and synchronous entry points disagree"
     if rank == 0:
         sampler.resume()
-    e2e = {"value": world * B * K / e2e_s, "unit": UNIT,
+    best = min(pipe_runs) if pipe_runs else e2e_s
+    e2e = {"value": world * B * K / best, "unit": UNIT,
            "h2d_bytes_per_step": int(skel_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
-           "policy": f"fastest of {E2E_REPEATS} repetitions of {K} steps",
-           "all_repetitions": [world * B * K / t for t in e2e_runs]}
+           "policy": (f"fastest of {E2E_REPEATS} repetitions of {K} steps through Segmenter.submit / wait (two batches in "
+                      "flight; each step's H2D and D2H inside the timed region)") if pipe_runs else
+                     f"fastest of {E2E_REPEATS} repetitions of {K} steps",
+           "all_repetitions": [world * B * K / t for t in (pipe_runs or e2e_runs)],
+           "one_call_at_a_time": sync_call}
 
     # ---- dominant kernel -> roofline --------------------------------------------
     roofline = None

@@ -209,6 +209,8 @@ int alloc_workspace(Ctx *ctx) {
     if ((rc = dmalloc(ctx, &ctx->d_skel, rows * c.in_channels))) return rc;
     if ((rc = dmalloc(ctx, &ctx->d_logits, frames * c.num_classes))) return rc;
     if ((rc = dmalloc(ctx, &ctx->d_labels, frames))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_logits2, frames * c.num_classes))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_labels2, frames))) return rc;
     return GS_OK;
 }
 
@@ -219,7 +221,7 @@ void free_ctx(Ctx *ctx) {
     align_embed_destroy(ctx);
     void *ptrs[] = {ctx->headWT, ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
                     ctx->bufU[1], ctx->PT, ctx->PV, ctx->PVpart, ctx->seS, ctx->gT, ctx->gV, ctx->d_skel,
-                    ctx->d_logits, ctx->d_labels, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
+                    ctx->d_logits, ctx->d_labels, ctx->d_logits2, ctx->d_labels2, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
                     ctx->d_al_path, ctx->d_al_plen};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -228,6 +230,9 @@ void free_ctx(Ctx *ctx) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
     }
     for (cudaEvent_t e : ctx->ev_front)
+        if (e) cudaEventDestroy(e);
+    if (ctx->pipe_d2h) cudaStreamDestroy(ctx->pipe_d2h);
+    for (cudaEvent_t e : {ctx->ev_pipe_front, ctx->ev_pipe_head[0], ctx->ev_pipe_head[1], ctx->ev_pipe_done[0], ctx->ev_pipe_done[1]})
         if (e) cudaEventDestroy(e);
     for (ProfSlot &ps : ctx->prof.pool) {
         cudaEventDestroy(ps.e0);
@@ -260,6 +265,7 @@ int check_segment_args(Ctx *ctx, const void *in, int B, int T) {
 
 // workspace ordering between calls on different streams (Ctx::ev_last)
 int order_after_previous(Ctx *ctx, cudaStream_t st) {
+    ctx->pipe_chain = false;      // any entry point but gs_segment_host_submit breaks a chain of submits
     if (ctx->ev_last_valid && ctx->last_stream != st) GS_CUDA(cudaStreamWaitEvent(st, ctx->ev_last, 0));
     return GS_OK;
 }
@@ -328,6 +334,18 @@ int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weight
         for (int i = 0; i < 2; ++i) {
             if (cudaStreamCreateWithFlags(&ctx->own_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("stream/event creation failed");
+                rc = GS_ERR_CUDA;
+                break;
+            }
+        }
+        {
+            bool ok = cudaStreamCreateWithFlags(&ctx->pipe_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&ctx->ev_pipe_front, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < 2 && ok; ++i)
+                ok = cudaEventCreateWithFlags(&ctx->ev_pipe_head[i], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ctx->ev_pipe_done[i], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) {
                 set_error("stream/event creation failed");
                 rc = GS_ERR_CUDA;
                 break;
@@ -513,6 +531,90 @@ int gs_segment_host(gs_ctx *h, const float *skel_host, float *logits_host, uint8
     ctx->ev_valid = true;
     if ((rc = mark_done(ctx, sc))) return rc;
     GS_CUDA(cudaStreamSynchronize(sc));
+    return GS_OK;
+}
+
+int gs_segment_host_submit(gs_ctx *h, const float *skel_host, float *logits_host, uint8_t *labels_host, int B, int T,
+                           int *ticket) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_segment_args(ctx, skel_host, B, T);
+    if (rc) return rc;
+    if (!ticket || (!logits_host && !labels_host)) {
+        set_error("gs_segment_host_submit: ticket and at least one output buffer must be set");
+        return GS_ERR_INVALID;
+    }
+    if (ctx->cfg.precision != GS_PREC_BF16) {
+        set_error("gs_segment_host_submit: bf16 contexts only (the fp32 path has the synchronous entry point)");
+        return GS_ERR_UNSUPPORTED;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    const gs_config &c = ctx->cfg;
+    const size_t in_per = (size_t)T * c.num_joints * c.in_channels;
+    const size_t out_per = (size_t)T * c.num_classes;
+    cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1], sd = ctx->pipe_d2h;
+    const int slot = (int)(ctx->pipe_next & 1);
+    // at most two batches in flight: the batch that used this slot (ticket - 2) must be complete, its device output
+    // buffer and the caller's host buffers of that batch are then free
+    if (ctx->pipe_done_valid[slot]) GS_CUDA(cudaEventSynchronize(ctx->ev_pipe_done[slot]));
+    const bool chained = ctx->pipe_chain;
+    if (!chained) {
+        // first submit after another entry point: order all three streams behind that call
+        if (ctx->ev_last_valid) {
+            GS_CUDA(cudaStreamWaitEvent(sc, ctx->ev_last, 0));
+            GS_CUDA(cudaStreamWaitEvent(sx, ctx->ev_last, 0));
+            GS_CUDA(cudaStreamWaitEvent(sd, ctx->ev_last, 0));
+        }
+    } else if (ctx->pipe_front_valid) {
+        // the previous batch's input kernels must have read d_skel before it is overwritten
+        GS_CUDA(cudaStreamWaitEvent(sx, ctx->ev_pipe_front, 0));
+    }
+    const int nch = B >= 4 * Ctx::kFrontChunks ? Ctx::kFrontChunks : 1;
+    const int per = (B + nch - 1) / nch;
+    ctx->front_nchunks = 0;
+    for (int k = 0, b0 = 0; b0 < B; ++k, b0 += per) {
+        const int nb = (B - b0) < per ? (B - b0) : per;
+        GS_CUDA(cudaMemcpyAsync(ctx->d_skel + b0 * in_per, skel_host + b0 * in_per, nb * in_per * 4,
+                                cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaEventRecord(ctx->ev_front[k], sx));
+        ctx->front_b0[k] = b0;
+        ctx->front_nb[k] = nb;
+        ctx->front_nchunks = k + 1;
+    }
+    float *dl = slot ? ctx->d_logits2 : ctx->d_logits;
+    uint8_t *db = slot ? ctx->d_labels2 : ctx->d_labels;
+    rc = forward(ctx, ctx->d_skel, dl, labels_host ? db : nullptr, B, T, -1, nullptr, sc);
+    ctx->front_nchunks = 0;
+    if (rc) return rc;
+    ctx->pipe_front_valid = true;             // recorded by the forward pass behind its input kernels
+    GS_CUDA(cudaEventRecord(ctx->ev_pipe_head[slot], sc));
+    GS_CUDA(cudaStreamWaitEvent(sd, ctx->ev_pipe_head[slot], 0));
+    if (logits_host) GS_CUDA(cudaMemcpyAsync(logits_host, dl, B * out_per * 4, cudaMemcpyDeviceToHost, sd));
+    if (labels_host) GS_CUDA(cudaMemcpyAsync(labels_host, db, (size_t)B * T, cudaMemcpyDeviceToHost, sd));
+    GS_CUDA(cudaEventRecord(ctx->ev_pipe_done[slot], sd));
+    ctx->pipe_done_valid[slot] = true;
+    // everything of this batch is behind ev_last (the result copy is the last thing it does)
+    if ((rc = mark_done(ctx, sd))) return rc;
+    ctx->pipe_chain = true;
+    *ticket = (int)(ctx->pipe_next & 0x7fffffff);
+    ctx->pipe_next += 1;
+    return GS_OK;
+}
+
+int gs_segment_host_wait(gs_ctx *h, int ticket) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx) {
+        set_error("gs_segment_host_wait: null context");
+        return GS_ERR_INVALID;
+    }
+    const long long next = ctx->pipe_next;
+    const long long t = (next & ~0x7fffffffLL) | (long long)(unsigned)ticket;
+    if (ticket < 0 || t >= next) {
+        set_error("gs_segment_host_wait: ticket %d was never issued", ticket);
+        return GS_ERR_INVALID;
+    }
+    if (t < next - 2) return GS_OK;           // older batches were completed when their slot was reused
+    GS_CUDA(cudaSetDevice(ctx->device));
+    GS_CUDA(cudaEventSynchronize(ctx->ev_pipe_done[(int)(t & 1)]));
     return GS_OK;
 }
 

@@ -130,6 +130,16 @@ struct Ctx {
     static constexpr int kFrontChunks = 4;
     cudaEvent_t ev_front[kFrontChunks] = {nullptr, nullptr, nullptr, nullptr};
     int front_nchunks = 0, front_b0[kFrontChunks] = {0, 0, 0, 0}, front_nb[kFrontChunks] = {0, 0, 0, 0};
+    // gs_segment_host_submit / _wait: up to two batches in flight.  The input copy of batch n+1 runs under the kernels
+    // of batch n (it waits for ev_pipe_front: batch n's input kernels have consumed d_skel), the result copy of batch n
+    // runs on a third stream under the kernels of batch n+1 (outputs alternate between two device buffers).
+    cudaStream_t pipe_d2h = nullptr;
+    cudaEvent_t ev_pipe_front = nullptr, ev_pipe_head[2] = {nullptr, nullptr}, ev_pipe_done[2] = {nullptr, nullptr};
+    bool pipe_front_valid = false, pipe_done_valid[2] = {false, false};
+    float *d_logits2 = nullptr;
+    uint8_t *d_labels2 = nullptr;
+    long long pipe_next = 0;      // next ticket
+    bool pipe_chain = false;      // the previous entry-point call on this context was a submit (no cross-stream wait needed)
     bool ev_valid = false;
     // Every entry point shares this context's workspace, whatever stream it runs on: each call records
     // `ev_last` behind its work and the next call's stream(s) wait for it first, so sequential calls from

@@ -474,6 +474,8 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
                 }
                 GS_KERNEL_CHECK();
             }
+            // host entry points: the staged input has been consumed (gs_segment_host_submit overwrites it for the next batch)
+            if (ctx->front_nchunks > 0) GS_CUDA(cudaEventRecord(ctx->ev_pipe_front, st));
         } else {
             gcn::LaunchGcn L{};
             L.mapX = m.f_x_load;

@@ -346,7 +346,7 @@ struct StjCfg {
 };
 
 template <int V, int Q>
-__global__ void __launch_bounds__(kStjThreads, 1)
+__global__ void __launch_bounds__(kStjThreads, Q <= 2 ? 2 : 1)
 stj_tc_kernel(const float *__restrict__ PT, const float *__restrict__ PV, const float *__restrict__ seS, int B, int T,
               int ntT, int ctasT, const float *__restrict__ P1, const float *__restrict__ bW,
               const float *__restrict__ P2t, const float *__restrict__ bt, const float *__restrict__ P2v,
@@ -808,7 +808,9 @@ int launch_attention(Ctx *ctx, const BlockParams &bp, const TU *U, int B, int T,
     if (stj_packed && C == 4 * bp.cj && (C == 64 || C == 128 || C == 256)) {
         const int ntT = cdiv(T, kStjTcPos);
         const int itemsT = B * ntT, itemsV = cdiv(B, kStjClipsPerJointItem);
-        int grid = std::min(ctx->sm_count, itemsT + itemsV);
+        // two CTAs per SM at C <= 128 (17 / 40 KB of shared memory, 64 registers): an item is a chain of short phases
+        // between CTA barriers, and a second CTA fills the gaps
+        int grid = std::min(ctx->sm_count * (C <= 128 ? 2 : 1), itemsT + itemsV);
         int ctasV = (int)((double)grid * itemsV / (itemsT + itemsV) + 0.5);
         ctasV = std::max(1, std::min(ctasV, grid - 1));
         if (grid < 2) { grid = 2; ctasV = 1; }

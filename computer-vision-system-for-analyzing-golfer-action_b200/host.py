@@ -31,7 +31,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}
 # every symbol include/golfer_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
-    "gs_segment_host", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
+    "gs_segment_host", "gs_segment_host_submit", "gs_segment_host_wait", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
     "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
     "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
@@ -85,6 +85,8 @@ def load_library():
         L.gs_destroy.argtypes = [vp]
         L.gs_segment.argtypes = [vp, vp, vp, u8p, i32, i32, vp]
         L.gs_segment_host.argtypes = [vp, vp, vp, u8p, i32, i32]
+        L.gs_segment_host_submit.argtypes = [vp, vp, vp, u8p, i32, i32, ctypes.POINTER(ctypes.c_int)]
+        L.gs_segment_host_wait.argtypes = [vp, i32]
         L.gs_segment_features.argtypes = [vp, vp, i32, vp, i32, i32, vp]
         L.gs_align.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.gs_align_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
@@ -112,7 +114,8 @@ def load_library():
                                             ctypes.POINTER(ctypes.c_int64)]
         for name in ("gs_profile_enable", "gs_profile_reset", "gs_profile_read", "gs_profile_read_block"):
             getattr(L, name).restype = ctypes.c_int
-        for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host",
+        for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host", "gs_segment_host_submit",
+                     "gs_segment_host_wait",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
                      "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed"):
             getattr(L, name).restype = ctypes.c_int
@@ -228,6 +231,14 @@ class Context:
             pass
 
 
+class Ticket:
+    """One batch in flight behind Segmenter.submit: keeps the host buffers alive until it has been waited for."""
+    __slots__ = ("id", "skel", "logits", "labels")
+
+    def __init__(self, tid, skel, logits, labels):
+        self.id, self.skel, self.logits, self.labels = tid, skel, logits, labels
+
+
 class Segmenter:
     """segment(skel[B,T,V,C]) -> logits[B,T,K] on one B200.
 
@@ -293,6 +304,54 @@ class Segmenter:
         return (logits, labels) if return_labels else logits
 
     __call__ = segment
+
+    # -- pipelined host entry point ----------------------------------------
+    def submit(self, skel, logits_out=None, labels_out=None) -> "Ticket":
+        """Enqueue one HOST batch and return at once (gs_segment_host_submit): the input copy of this batch overlaps
+        the kernels of the previous one, its result copy overlaps the kernels of the next one; at most two batches
+        are in flight (a third submit first waits for the oldest).  `skel` must be a pinned fp32 host tensor
+        [B,T,V,C] that stays untouched until `wait`; `logits_out` / `labels_out` are pinned host tensors to fill
+        (allocated when omitted).  Returns a ticket for `wait`."""
+        torch = _torch()
+        if not isinstance(skel, torch.Tensor) or skel.is_cuda or skel.dtype != torch.float32 or not skel.is_contiguous():
+            raise GolferError("submit: skel must be a contiguous fp32 host tensor (pinned for overlap)")
+        B, T = self._shape(skel.shape)
+        K = self.cfg.num_classes
+        if logits_out is None:
+            logits_out = torch.empty((B, T, K), dtype=torch.float32, pin_memory=True)
+        if (logits_out.is_cuda or logits_out.dtype != torch.float32 or tuple(logits_out.shape) != (B, T, K)
+                or not logits_out.is_contiguous()):
+            raise GolferError(f"submit: logits_out must be a contiguous host fp32 tensor of shape {(B, T, K)}")
+        if labels_out is not None and (labels_out.is_cuda or labels_out.dtype != torch.uint8
+                                       or tuple(labels_out.shape) != (B, T) or not labels_out.is_contiguous()):
+            raise GolferError(f"submit: labels_out must be a contiguous host u8 tensor of shape {(B, T)}")
+        tk = ctypes.c_int(-1)
+        _check(self.ctx._L.gs_segment_host_submit(self.ctx.handle, skel.data_ptr(), logits_out.data_ptr(),
+                                                  labels_out.data_ptr() if labels_out is not None else None, B, T,
+                                                  ctypes.byref(tk)), "gs_segment_host_submit")
+        return Ticket(tk.value, skel, logits_out, labels_out)
+
+    def wait(self, ticket: "Ticket"):
+        """Block until the batch behind `ticket` is complete; returns (logits, labels) host tensors."""
+        _check(self.ctx._L.gs_segment_host_wait(self.ctx.handle, ticket.id), "gs_segment_host_wait")
+        return ticket.logits, ticket.labels
+
+    def segment_stream(self, batches, return_labels: bool = False):
+        """Generator over an iterable of pinned host batches: yields each batch's logits (and labels) in order while
+        the next batch is already copying and computing."""
+        torch = _torch()
+        prev = None
+        for x in batches:
+            B, T = self._shape(x.shape)
+            lab = torch.empty((B, T), dtype=torch.uint8, pin_memory=True) if return_labels else None
+            tk = self.submit(x, None, lab)
+            if prev is not None:
+                lo, la = self.wait(prev)
+                yield (lo, la) if return_labels else lo
+            prev = tk
+        if prev is not None:
+            lo, la = self.wait(prev)
+            yield (lo, la) if return_labels else lo
 
     def features(self, skel, block: int):
         """Block output after both attention gates, fp32 [B,T,V,C] (parity hook)."""

@@ -98,6 +98,16 @@ int gs_segment(gs_ctx *ctx, const float *skel_dev, float *logits_dev, uint8_t *l
 int gs_segment_host(gs_ctx *ctx, const float *skel_host, float *logits_host,
                     uint8_t *labels_host, int B, int T);
 
+/* Pipelined form of gs_segment_host for a stream of batches (GS_PREC_BF16 contexts): _submit enqueues the copies and
+ * kernels of one batch and returns at once with a ticket; _wait returns when that batch's results are in its host
+ * buffers.  Up to two batches are in flight: the input copy of batch n+1 overlaps the kernels of batch n, the result
+ * copy of batch n overlaps the kernels of batch n+1 (a third submit first waits for the oldest batch).  The host
+ * buffers of a batch (pinned memory, or the copies do not overlap) must stay untouched until its _wait returns.
+ * Any other entry point may follow a submit; it runs after every batch submitted so far. */
+int gs_segment_host_submit(gs_ctx *ctx, const float *skel_host, float *logits_host,
+                           uint8_t *labels_host, int B, int T, int *ticket);
+int gs_segment_host_wait(gs_ctx *ctx, int ticket);
+
 /* Debug / parity hook: run the network through block `block` (0-based) and write that
  * block's output AFTER both attention gates as fp32 [B,T,V,C_block] to out_dev. */
 int gs_segment_features(gs_ctx *ctx, const float *skel_dev, int block, float *out_dev,

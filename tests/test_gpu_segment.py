@@ -217,6 +217,38 @@ def test_determinism_and_batch_independence(prec):
     seg.ctx.close()
 
 
+def test_pipelined_host_entry_point_matches_synchronous_one():
+    """submit / wait keeps two batches in flight (copies of one under the kernels of the other): every batch's result
+    must equal the synchronous entry point's bit for bit, also when other entry points run in between."""
+    cfg = golfer_b200.V0
+    seg = golfer_b200.Segmenter(cfg, precision="bf16", max_B=20, max_T=60)
+    batches = [torch.from_numpy(osegnet.synth_skeletons(B, T, cfg, seed=40 + i)).pin_memory()
+               for i, (B, T) in enumerate([(20, 60), (16, 60), (20, 33), (3, 60), (20, 60), (17, 48)])]
+    want = [seg.segment(x, return_labels=True) for x in batches]
+    got = list(seg.segment_stream(batches, return_labels=True))
+    assert len(got) == len(want)
+    for (wl, wb), (gl, gb) in zip(want, got):
+        assert torch.equal(wl, gl) and torch.equal(wb, gb)
+    # three submits before the first wait (the third waits for the first inside the library), a device call and a
+    # synchronous host call between submits
+    t0 = seg.submit(batches[0])
+    t1 = seg.submit(batches[1])
+    t2 = seg.submit(batches[2])
+    dev = seg.segment(batches[3].cuda())
+    t3 = seg.submit(batches[4])
+    sync_logits = seg.segment(batches[5])
+    for tk, i in ((t0, 0), (t1, 1), (t2, 2), (t3, 4)):
+        assert torch.equal(seg.wait(tk)[0], want[i][0])
+    assert torch.equal(dev.cpu(), want[3][0]) and torch.equal(sync_logits, want[5][0])
+    with pytest.raises(golfer_b200.GolferError):
+        seg.submit(batches[0].cuda())
+    fp32 = golfer_b200.Segmenter(cfg, precision="fp32", max_B=4, max_T=16)
+    with pytest.raises(golfer_b200.GolferError):
+        fp32.submit(torch.zeros(2, 16, 17, 3).pin_memory())
+    fp32.ctx.close()
+    seg.ctx.close()
+
+
 def test_bad_shapes_raise():
     seg = golfer_b200.Segmenter(golfer_b200.V0, precision="fp32", max_B=2, max_T=8)
     with pytest.raises(golfer_b200.GolferError):
