@@ -222,7 +222,7 @@ void free_ctx(Ctx *ctx) {
     void *ptrs[] = {ctx->headWT, ctx->d_blob, ctx->bufX, ctx->bufXA, ctx->bufY, ctx->bufH, ctx->bufR, ctx->bufU[0],
                     ctx->bufU[1], ctx->PT, ctx->PV, ctx->PVpart, ctx->seS, ctx->gT, ctx->gV, ctx->d_skel,
                     ctx->d_logits, ctx->d_labels, ctx->d_logits2, ctx->d_labels2, ctx->align_ws, ctx->d_al_a, ctx->d_al_b, ctx->d_al_cost,
-                    ctx->d_al_path, ctx->d_al_plen};
+                    ctx->d_al_path, ctx->d_al_plen, ctx->al2_a, ctx->al2_b, ctx->al2_cost, ctx->al2_path, ctx->al2_plen};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -232,7 +232,8 @@ void free_ctx(Ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_front)
         if (e) cudaEventDestroy(e);
     if (ctx->pipe_d2h) cudaStreamDestroy(ctx->pipe_d2h);
-    for (cudaEvent_t e : {ctx->ev_pipe_front, ctx->ev_pipe_head[0], ctx->ev_pipe_head[1], ctx->ev_pipe_done[0], ctx->ev_pipe_done[1]})
+    for (cudaEvent_t e : {ctx->ev_pipe_front, ctx->ev_pipe_head[0], ctx->ev_pipe_head[1], ctx->ev_pipe_done[0], ctx->ev_pipe_done[1],
+                          ctx->ev_al_chunk[0], ctx->ev_al_chunk[1], ctx->ev_al_done[0], ctx->ev_al_done[1]})
         if (e) cudaEventDestroy(e);
     for (ProfSlot &ps : ctx->prof.pool) {
         cudaEventDestroy(ps.e0);
@@ -265,7 +266,8 @@ int check_segment_args(Ctx *ctx, const void *in, int B, int T) {
 
 // workspace ordering between calls on different streams (Ctx::ev_last)
 int order_after_previous(Ctx *ctx, cudaStream_t st) {
-    ctx->pipe_chain = false;      // any entry point but gs_segment_host_submit breaks a chain of submits
+    ctx->pipe_chain = false;      // any entry point but the matching submit breaks a chain of submits
+    ctx->al_pipe_chain = false;
     if (ctx->ev_last_valid && ctx->last_stream != st) GS_CUDA(cudaStreamWaitEvent(st, ctx->ev_last, 0));
     return GS_OK;
 }
@@ -344,7 +346,9 @@ int gs_create(gs_ctx **out, int device, const gs_config *cfg, const void *weight
                       cudaEventCreateWithFlags(&ctx->ev_pipe_front, cudaEventDisableTiming) == cudaSuccess;
             for (int i = 0; i < 2 && ok; ++i)
                 ok = cudaEventCreateWithFlags(&ctx->ev_pipe_head[i], cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ctx->ev_pipe_done[i], cudaEventDisableTiming) == cudaSuccess;
+                     cudaEventCreateWithFlags(&ctx->ev_pipe_done[i], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ctx->ev_al_chunk[i], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ctx->ev_al_done[i], cudaEventDisableTiming) == cudaSuccess;
             if (!ok) {
                 set_error("stream/event creation failed");
                 rc = GS_ERR_CUDA;
@@ -595,6 +599,7 @@ int gs_segment_host_submit(gs_ctx *h, const float *skel_host, float *logits_host
     // everything of this batch is behind ev_last (the result copy is the last thing it does)
     if ((rc = mark_done(ctx, sd))) return rc;
     ctx->pipe_chain = true;
+    ctx->al_pipe_chain = false;
     *ticket = (int)(ctx->pipe_next & 0x7fffffff);
     ctx->pipe_next += 1;
     return GS_OK;
@@ -737,6 +742,94 @@ int gs_align_host(gs_ctx *h, const float *a_host, const float *b_host, int N, in
     ctx->ev_valid = true;
     if ((rc = mark_done(ctx, sc))) return rc;
     GS_CUDA(cudaStreamSynchronize(sc));
+    return GS_OK;
+}
+
+int gs_align_host_submit(gs_ctx *h, const float *a_host, const float *b_host, int N, int Ta, int Tb, int V, int Cc,
+                         float *cost_host, int32_t *path_host, int32_t *path_len_host, int *ticket) {
+    Ctx *ctx = (Ctx *)h;
+    int rc = check_align_args(ctx, a_host, b_host, N, Ta, Tb, V, Cc);
+    if (rc) return rc;
+    if (!ticket || !cost_host || ((path_host == nullptr) != (path_len_host == nullptr))) {
+        set_error("ticket and cost_host must be set; path_host and path_len_host must both be set or both NULL");
+        return GS_ERR_INVALID;
+    }
+    GS_CUDA(cudaSetDevice(ctx->device));
+    const int slot = (int)(ctx->al_pipe_next & 1);
+    // at most two batches in flight: the batch that used this set of staging buffers (ticket - 2) must be complete
+    if (ctx->al_done_valid[slot]) GS_CUDA(cudaEventSynchronize(ctx->ev_al_done[slot]));
+    const size_t na = (size_t)N * Ta * V * Cc, nb = (size_t)N * Tb * V * Cc;
+    const size_t maxL = (size_t)Ta + Tb - 1;
+    float **pa = slot ? &ctx->al2_a : &ctx->d_al_a, **pb = slot ? &ctx->al2_b : &ctx->d_al_b;
+    float **pc = slot ? &ctx->al2_cost : &ctx->d_al_cost;
+    int32_t **pp = slot ? &ctx->al2_path : &ctx->d_al_path, **pl = slot ? &ctx->al2_plen : &ctx->d_al_plen;
+    size_t *cap = slot ? ctx->al2_cap : ctx->al_host_cap;
+    if ((rc = grow(ctx, pa, &cap[0], na))) return rc;
+    if ((rc = grow(ctx, pb, &cap[1], nb))) return rc;
+    if ((rc = grow(ctx, pc, &cap[2], (size_t)N))) return rc;
+    if (path_host) {
+        if ((rc = grow(ctx, pp, &cap[3], (size_t)N * maxL * 2))) return rc;
+        if ((rc = grow(ctx, pl, &cap[4], (size_t)N))) return rc;
+    }
+    int per = N;          // chunks of whole sweep rounds, as in gs_align_host
+    if (N >= 64) {
+        const int m = (N + 16 * ctx->sm_count - 1) / (16 * ctx->sm_count);
+        per = m * ctx->sm_count;
+        if (N < 4 * per) per = (N + 3) / 4;
+    }
+    cudaStream_t sc = ctx->own_stream[0], sx = ctx->own_stream[1], sd = ctx->pipe_d2h;
+    if (!ctx->al_pipe_chain && ctx->ev_last_valid) {
+        // first submit after another entry point: order all three streams behind that call
+        GS_CUDA(cudaStreamWaitEvent(sc, ctx->ev_last, 0));
+        GS_CUDA(cudaStreamWaitEvent(sx, ctx->ev_last, 0));
+        GS_CUDA(cudaStreamWaitEvent(sd, ctx->ev_last, 0));
+    }
+    for (int k = 0, n0 = 0; n0 < N; ++k, n0 += per) {
+        const int cnt = (N - n0) < per ? (N - n0) : per;
+        const int e = k & 1;
+        const size_t oa = (size_t)n0 * Ta * V * Cc, ob = (size_t)n0 * Tb * V * Cc;
+        GS_CUDA(cudaMemcpyAsync(*pa + oa, a_host + oa, (size_t)cnt * Ta * V * Cc * 4, cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaMemcpyAsync(*pb + ob, b_host + ob, (size_t)cnt * Tb * V * Cc * 4, cudaMemcpyHostToDevice, sx));
+        GS_CUDA(cudaEventRecord(ctx->ev_copy[e], sx));
+        GS_CUDA(cudaStreamWaitEvent(sc, ctx->ev_copy[e], 0));
+        rc = align_launch(ctx, *pa + oa, *pb + ob, cnt, Ta, Tb, V, Cc, *pc + n0,
+                          path_host ? *pp + (size_t)n0 * maxL * 2 : nullptr, path_host ? *pl + n0 : nullptr, sc);
+        if (rc) return rc;
+        // results leave on the third stream: the next chunk's sweep does not wait for them
+        GS_CUDA(cudaEventRecord(ctx->ev_al_chunk[e], sc));
+        GS_CUDA(cudaStreamWaitEvent(sd, ctx->ev_al_chunk[e], 0));
+        GS_CUDA(cudaMemcpyAsync(cost_host + n0, *pc + n0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sd));
+        if (path_host) {
+            GS_CUDA(cudaMemcpyAsync(path_host + (size_t)n0 * maxL * 2, *pp + (size_t)n0 * maxL * 2, (size_t)cnt * maxL * 8,
+                                    cudaMemcpyDeviceToHost, sd));
+            GS_CUDA(cudaMemcpyAsync(path_len_host + n0, *pl + n0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, sd));
+        }
+    }
+    GS_CUDA(cudaEventRecord(ctx->ev_al_done[slot], sd));
+    ctx->al_done_valid[slot] = true;
+    if ((rc = mark_done(ctx, sd))) return rc;      // the last result copy is the last thing this batch does
+    ctx->al_pipe_chain = true;
+    ctx->pipe_chain = false;
+    *ticket = (int)(ctx->al_pipe_next & 0x7fffffff);
+    ctx->al_pipe_next += 1;
+    return GS_OK;
+}
+
+int gs_align_host_wait(gs_ctx *h, int ticket) {
+    Ctx *ctx = (Ctx *)h;
+    if (!ctx) {
+        set_error("gs_align_host_wait: null context");
+        return GS_ERR_INVALID;
+    }
+    const long long next = ctx->al_pipe_next;
+    const long long t = (next & ~0x7fffffffLL) | (long long)(unsigned)ticket;
+    if (ticket < 0 || t >= next) {
+        set_error("gs_align_host_wait: ticket %d was never issued", ticket);
+        return GS_ERR_INVALID;
+    }
+    if (t < next - 2) return GS_OK;           // older batches were completed when their buffers were reused
+    GS_CUDA(cudaSetDevice(ctx->device));
+    GS_CUDA(cudaEventSynchronize(ctx->ev_al_done[(int)(t & 1)]));
     return GS_OK;
 }
 

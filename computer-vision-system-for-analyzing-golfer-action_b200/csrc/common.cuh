@@ -140,6 +140,15 @@ struct Ctx {
     uint8_t *d_labels2 = nullptr;
     long long pipe_next = 0;      // next ticket
     bool pipe_chain = false;      // the previous entry-point call on this context was a submit (no cross-stream wait needed)
+    // gs_align_host_submit / _wait: the same for the alignment (two batches in flight, two sets of staging buffers;
+    // the call is bound by the input copy, so what the pipeline hides is the last chunk's sweep and result copy)
+    float *al2_a = nullptr, *al2_b = nullptr, *al2_cost = nullptr;
+    int32_t *al2_path = nullptr, *al2_plen = nullptr;
+    size_t al2_cap[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev_al_chunk[2] = {nullptr, nullptr}, ev_al_done[2] = {nullptr, nullptr};
+    bool al_done_valid[2] = {false, false};
+    long long al_pipe_next = 0;
+    bool al_pipe_chain = false;
     bool ev_valid = false;
     // Every entry point shares this context's workspace, whatever stream it runs on: each call records
     // `ev_last` behind its work and the next call's stream(s) wait for it first, so sequential calls from

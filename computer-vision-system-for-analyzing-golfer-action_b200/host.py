@@ -31,7 +31,7 @@ PRECISIONS = {"fp32": 0, "bf16": 1}
 # every symbol include/golfer_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = (
     "gs_abi_version", "gs_last_error", "gs_create", "gs_destroy", "gs_segment",
-    "gs_segment_host", "gs_segment_host_submit", "gs_segment_host_wait", "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
+    "gs_segment_host", "gs_segment_host_submit", "gs_segment_host_wait", "gs_segment_features", "gs_align", "gs_align_host", "gs_align_host_submit", "gs_align_host_wait", "gs_pair_cost",
     "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed", "gs_launch_count", "gs_workspace_bytes", "gs_last_kernel_ms",
     "gs_profile_enable", "gs_profile_reset", "gs_profile_kernels", "gs_profile_read", "gs_profile_read_block", "gs_debug_read",
 )
@@ -90,6 +90,8 @@ def load_library():
         L.gs_segment_features.argtypes = [vp, vp, i32, vp, i32, i32, vp]
         L.gs_align.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
         L.gs_align_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        L.gs_align_host_submit.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, ctypes.POINTER(ctypes.c_int)]
+        L.gs_align_host_wait.argtypes = [vp, i32]
         L.gs_pair_cost.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_compare.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.gs_normalize_pose.argtypes = [vp, vp, vp, i32, i32, i32, ctypes.c_float, vp]
@@ -115,7 +117,7 @@ def load_library():
         for name in ("gs_profile_enable", "gs_profile_reset", "gs_profile_read", "gs_profile_read_block"):
             getattr(L, name).restype = ctypes.c_int
         for name in ("gs_create", "gs_destroy", "gs_segment", "gs_segment_host", "gs_segment_host_submit",
-                     "gs_segment_host_wait",
+                     "gs_segment_host_wait", "gs_align_host_submit", "gs_align_host_wait",
                      "gs_segment_features", "gs_align", "gs_align_host", "gs_pair_cost",
                      "gs_compare", "gs_normalize_pose", "gs_align_phase", "gs_set_align_encoder", "gs_align_embed"):
             getattr(L, name).restype = ctypes.c_int
@@ -451,6 +453,46 @@ def align_batch(a, b, ctx: Optional[Context] = None, want_path: bool = True):
                                         cost.data_ptr(), path.data_ptr() if want_path else None,
                                         plen.data_ptr() if want_path else None), "gs_align_host")
     return cost, path, plen
+
+
+class AlignTicket:
+    """One alignment batch in flight behind align_submit: keeps its host buffers alive until align_wait."""
+    __slots__ = ("id", "ctx", "a", "b", "cost", "path", "plen")
+
+    def __init__(self, tid, ctx, a, b, cost, path, plen):
+        self.id, self.ctx, self.a, self.b, self.cost, self.path, self.plen = tid, ctx, a, b, cost, path, plen
+
+
+def align_submit(a, b, ctx: Optional[Context] = None, want_path: bool = True, device: int = 0) -> AlignTicket:
+    """Pipelined host alignment (gs_align_host_submit): a [N,Ta,V,Cc], b [N,Tb,V,Cc] contiguous fp32 HOST tensors
+    (pinned for overlap) -> a ticket; at most two batches in flight, the copies of one under the sweep of the other.
+    `align_wait(ticket)` returns (cost, path, path_len) host tensors."""
+    torch = _torch()
+    for name, t in (("a", a), ("b", b)):
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise GolferError(f"align_submit: {name} must be a contiguous fp32 host tensor (pinned for overlap)")
+    if a.dim() != 4 or b.dim() != 4 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise GolferError(f"align expects a [N,Ta,V,Cc] and b [N,Tb,V,Cc]; got {tuple(a.shape)} {tuple(b.shape)}")
+    N, Ta, V, Cc = (int(s) for s in a.shape)
+    Tb = int(b.shape[1])
+    if N < 1 or Cc < 2 or Ta < 1 or Tb < 1:
+        raise GolferError("align_submit needs at least one pair, one frame per sequence and (x, y) channels")
+    ctx = ctx or _align_ctx(device)
+    maxL = Ta + Tb - 1
+    cost = torch.empty((N,), dtype=torch.float32, pin_memory=True)
+    path = torch.empty((N, maxL, 2), dtype=torch.int32, pin_memory=True) if want_path else None
+    plen = torch.empty((N,), dtype=torch.int32, pin_memory=True) if want_path else None
+    tk = ctypes.c_int(-1)
+    _check(ctx._L.gs_align_host_submit(ctx.handle, a.data_ptr(), b.data_ptr(), N, Ta, Tb, V, Cc, cost.data_ptr(),
+                                       path.data_ptr() if want_path else None,
+                                       plen.data_ptr() if want_path else None, ctypes.byref(tk)),
+           "gs_align_host_submit")
+    return AlignTicket(tk.value, ctx, a, b, cost, path, plen)
+
+
+def align_wait(ticket: AlignTicket):
+    _check(ticket.ctx._L.gs_align_host_wait(ticket.ctx.handle, ticket.id), "gs_align_host_wait")
+    return ticket.cost, ticket.path, ticket.plen
 
 
 def align(a, b):

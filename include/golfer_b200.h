@@ -155,6 +155,15 @@ int gs_align_host(gs_ctx *ctx, const float *a_host, const float *b_host, int N, 
                   int Tb, int V, int Cc, float *cost_host, int32_t *path_host,
                   int32_t *path_len_host);
 
+/* Pipelined form of gs_align_host for a stream of batches (as gs_segment_host_submit / _wait): _submit enqueues one
+ * batch and returns a ticket, _wait returns when its results are in its host buffers; two batches in flight on two
+ * sets of staging buffers.  The call is bound by the input copy; the pipeline hides the last chunk's sweep and the
+ * result copy behind the next batch's input copy. */
+int gs_align_host_submit(gs_ctx *ctx, const float *a_host, const float *b_host, int N, int Ta,
+                         int Tb, int V, int Cc, float *cost_host, int32_t *path_host,
+                         int32_t *path_len_host, int *ticket);
+int gs_align_host_wait(gs_ctx *ctx, int ticket);
+
 /* Materialise the pairwise cost matrices only: cost_matrix_dev [N,Ta,Tb] fp32
  * (debug / parity hook for oracle/align.py:pair_cost). */
 int gs_pair_cost(gs_ctx *ctx, const float *a_dev, const float *b_dev, int N, int Ta, int Tb,

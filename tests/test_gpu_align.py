@@ -117,6 +117,29 @@ def test_host_entry_point_many_chunks():
     assert np.array_equal(cost_d.cpu().numpy(), rc) and np.array_equal(path_d.cpu().numpy(), rp)
 
 
+def test_pipelined_host_entry_point_matches_oracle():
+    """align_submit / align_wait: two batches in flight on two sets of staging buffers, other entry points in between."""
+    ctx = golfer_b200.host.Context(0)
+    shapes = [(300, 24, 20), (64, 33, 40), (310, 24, 20), (5, 17, 9), (300, 24, 20)]
+    data = []
+    for i, (N, Ta, Tb) in enumerate(shapes):
+        a, b = oalign.synth_swings(N, Ta, Tb, seed=60 + i)
+        data.append((torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(),
+                     align_native.align_batch_c(a, b, 4)))
+    tks = [golfer_b200.host.align_submit(a, b, ctx=ctx) for a, b, _ in data[:3]]     # the third waits for the first inside
+    dev_cost, dev_path, _ = golfer_b200.host.align_batch(data[3][0].cuda(), data[3][1].cuda(), ctx=ctx)
+    tks.append(golfer_b200.host.align_submit(data[4][0], data[4][1], ctx=ctx, want_path=False))
+    for tk, (_, _, (rc, rp, rl)) in zip(tks[:3], data[:3]):
+        cost, path, plen = golfer_b200.host.align_wait(tk)
+        assert np.array_equal(cost.numpy(), rc) and np.array_equal(path.numpy(), rp) and np.array_equal(plen.numpy(), rl)
+    assert np.array_equal(dev_cost.cpu().numpy(), data[3][2][0]) and np.array_equal(dev_path.cpu().numpy(), data[3][2][1])
+    cost, path, plen = golfer_b200.host.align_wait(tks[3])
+    assert path is None and np.array_equal(cost.numpy(), data[4][2][0])
+    with pytest.raises(golfer_b200.GolferError):
+        golfer_b200.host.align_submit(data[0][0].cuda(), data[0][1], ctx=ctx)
+    ctx.close()
+
+
 def test_public_align_signature_single_pair():
     a, b = oalign.synth_swings(1, 30, 26, seed=2)
     cost, path = golfer_b200.align(_dev(a[0]), _dev(b[0]))
