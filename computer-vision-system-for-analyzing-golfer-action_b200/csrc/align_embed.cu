@@ -2,8 +2,8 @@
 // Contract: oracle/embed.py (AlignEmbedConfig v0: per-frame MLP 34 -> 128 -> 128 over the (x, y) of the 17 joints,
 // cost c[i,j] = sqrt(max(|fa_i|^2 + |fb_j|^2 - 2 fa_i . fb_j, 0)), then the DP / tie-break / backtrack of align.cu).
 //
-//   embed_encoder_kernel   frames -> F [rows, 128] bf16 (the GEMM operand) + |F|^2 fp32 of the ROUNDED values
-//                          (CUDA cores, fp32: 20.7 kFMA per frame, weights in shared memory, 4 frames x 8 outputs per thread)
+//   embed_encoder_tc_kernel  frames -> F [rows, 128] bf16 (the GEMM operand) + |F|^2 fp32 of the ROUNDED values
+//                          (mma.sync m16n8k8 3xTF32 = fp32-accurate; both weight matrices as B fragments in shared memory)
 //   embed_cost_kernel      one CTA per (pair, 128-row tile, 128-column tile): D = Fa_tile . Fb_tile^T on tcgen05
 //                          (K = 128: 8 MMAs of M = N = 128, operands by TMA, accumulator in TMEM), epilogue
 //                          sqrt(max(na + nb - 2 D, 0)) staged through the (now dead) operand buffers so that rows leave
@@ -19,6 +19,7 @@ constexpr int kEmbIn = 34, kEmbHidden = 128, kEmbDim = 128;
 
 struct EmbedPath {
     float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr;    // device fp32
+    float *Wfrag = nullptr;           // W1 (K padded to 40) and W2 as 3xTF32 mma.sync B fragments (embed_encoder_tc_kernel)
     __nv_bfloat16 *F = nullptr;       // [N*(Ta+Tb) (+128 rows of slack), 128] embeddings of a then b
     float *norm = nullptr;            // [N*(Ta+Tb)]
     float *cm = nullptr;              // [N, ra, rb] cost matrices (when the caller does not take them)
@@ -30,92 +31,170 @@ namespace {
 using namespace tc;
 
 constexpr int kEncFrames = 128;       // frames per CTA pass of the encoder
-constexpr int kEncThreads = 512;      // 32 frame groups x 16 output groups: 4 frames x 8 outputs per thread
 
-// smem: W1 [34][128], b1[128], W2 [128][128], b2[128], x [128][34], h [128][128 + 4]: 166 KB, 16 warps per SM (the
-// 8-warp form ran at 28 % of the FMA pipe: shared-memory latency with nothing to hide it)
-__global__ void __launch_bounds__(kEncThreads)
-embed_encoder_kernel(const float *__restrict__ frames, int V, int Cc, size_t nframes, const float *__restrict__ W1,
-                     const float *__restrict__ b1, const float *__restrict__ W2, const float *__restrict__ b2,
-                     __nv_bfloat16 *__restrict__ F, float *__restrict__ norm) {
+// ---- the encoder on warp-level tensor cores: 3xTF32 (error-compensated: fp32 operands split into a TF32 head and a
+// TF32 tail, a.b = a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, the dropped term is 2^-22 relative), so the embeddings agree with
+// an fp32 evaluation to summation order and the parity policy of oracle/embed.py holds unchanged.  The first form of
+// this kernel was fp32 FMAs on CUDA cores (4 frames x 8 outputs per thread, weights in shared memory): 3.97 ms for the
+// 2.46 M frames of 4096 pairs, 37 % of the FMA pipe, bound by its shared-memory operand loads (6 loads per 32 FMAs);
+// this one: 2.14 ms.
+// One CTA pass = 128 frames, 8 warps x 16 frames (one m16 tile per warp); both weight matrices live in shared memory as
+// ready-made B fragments {hi(k=t), hi(k=t+4), lo(k=t), lo(k=t+4)} per (k-step, n-tile, lane): one conflict-free LDS.128
+// per three MMAs.  The hidden layer never leaves registers: accumulator tile j of layer 1 IS k-tile j of layer 2, its
+// A fragment is gathered inside each quad with 8 shuffles.
+constexpr int kEncTcThreads = 256;
+constexpr int kEncTcKs1 = 5;                     // K = 34 padded to 40
+constexpr int kEncLdx = 44;                      // sx row stride: conflict-free A-fragment loads
+constexpr size_t kEncFragFloats = (size_t)(kEncTcKs1 + kEmbHidden / 8) * (kEmbHidden / 8) * 32 * 4;   // 43008
+
+__device__ __forceinline__ uint32_t tf32_of(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kEncTcThreads, 1)
+embed_encoder_tc_kernel(const float *__restrict__ frames, int V, int Cc, size_t nframes, const float *__restrict__ Wfrag,
+                        const float *__restrict__ b1, const float *__restrict__ b2, __nv_bfloat16 *__restrict__ F,
+                        float *__restrict__ norm) {
     extern __shared__ __align__(16) float sm[];
-    float *sW1 = sm, *sb1 = sW1 + kEmbIn * kEmbHidden, *sW2 = sb1 + kEmbHidden, *sb2 = sW2 + kEmbHidden * kEmbDim;
-    float *sx = sb2 + kEmbDim, *sh = sx + kEncFrames * kEmbIn;
-    constexpr int ldh = kEmbHidden + 4;
-    for (int e = threadIdx.x; e < kEmbIn * kEmbHidden; e += kEncThreads) sW1[e] = W1[e];
-    for (int e = threadIdx.x; e < kEmbHidden * kEmbDim; e += kEncThreads) sW2[e] = W2[e];
+    float4 *fr1 = reinterpret_cast<float4 *>(sm);                       // [5][16][32]
+    float4 *fr2 = fr1 + kEncTcKs1 * 16 * 32;                            // [16][16][32]
+    float *sx = reinterpret_cast<float *>(fr2 + 16 * 16 * 32);          // [128][kEncLdx]
+    float *sb1 = sx + kEncFrames * kEncLdx, *sb2 = sb1 + kEmbHidden;
+    for (int e = threadIdx.x; e < (int)(kEncFragFloats / 4); e += kEncTcThreads)
+        fr1[e] = __ldg(reinterpret_cast<const float4 *>(Wfrag) + e);
     if (threadIdx.x < kEmbHidden) {
         sb1[threadIdx.x] = b1[threadIdx.x];
         sb2[threadIdx.x] = b2[threadIdx.x];
     }
-    const int fg = threadIdx.x >> 4, og = threadIdx.x & 15;       // 4 frames x 8 outputs per thread
+    for (int e = threadIdx.x; e < kEncFrames * kEncLdx; e += kEncTcThreads) sx[e] = 0.f;    // K padding stays zero
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    const int src_lo = (lane & ~3) | (t >> 1), src_hi = src_lo + 2;
+    const bool odd = t & 1;
     for (size_t f0 = (size_t)blockIdx.x * kEncFrames; f0 < nframes; f0 += (size_t)gridDim.x * kEncFrames) {
         __syncthreads();
         const int nf = (int)(nframes - f0 < (size_t)kEncFrames ? nframes - f0 : (size_t)kEncFrames);
-        for (int e = threadIdx.x; e < kEncFrames * kEmbIn; e += kEncThreads) {
+        for (int e = threadIdx.x; e < kEncFrames * kEmbIn; e += kEncTcThreads) {
             const int f = e / kEmbIn, k = e - f * kEmbIn;          // k = joint * 2 + (x | y)
-            sx[e] = f < nf ? frames[((f0 + f) * V + (k >> 1)) * Cc + (k & 1)] : 0.f;
+            sx[f * kEncLdx + k] = f < nf ? frames[((f0 + f) * V + (k >> 1)) * Cc + (k & 1)] : 0.f;
         }
         __syncthreads();
-        float acc[4][8];
+        // ---- layer 1: h = relu(x . W1 + b1), 16 n-tiles of 8 hidden units
+        float h[16][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int o = 0; o < 8; ++o) acc[a][o] = sb1[og * 8 + o];
-#pragma unroll 2
-        for (int k = 0; k < kEmbIn; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(sW1 + k * kEmbHidden + og * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(sW1 + k * kEmbHidden + og * 8 + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const float x = sx[(fg * 4 + a) * kEmbIn + k];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[a][o] = fmaf(x, w[o], acc[a][o]);
-            }
+        for (int nt = 0; nt < 16; ++nt) {
+            const float2 bb = *reinterpret_cast<const float2 *>(sb1 + nt * 8 + 2 * t);
+            h[nt][0] = h[nt][2] = bb.x;
+            h[nt][1] = h[nt][3] = bb.y;
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int ks = 0; ks < kEncTcKs1; ++ks) {
+            const float xa[4] = {sx[r0 * kEncLdx + ks * 8 + t], sx[r1 * kEncLdx + ks * 8 + t],
+                                 sx[r0 * kEncLdx + ks * 8 + t + 4], sx[r1 * kEncLdx + ks * 8 + t + 4]};
+            uint32_t ah[4], al[4];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) sh[(fg * 4 + a) * ldh + og * 8 + o] = fmaxf(acc[a][o], 0.f);
-        __syncthreads();
+            for (int i = 0; i < 4; ++i) {
+                ah[i] = tf32_of(xa[i]);
+                al[i] = tf32_of(xa[i] - __uint_as_float(ah[i]));
+            }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int o = 0; o < 8; ++o) acc[a][o] = sb2[og * 8 + o];
-#pragma unroll 4
-        for (int k = 0; k < kEmbHidden; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(sW2 + k * kEmbDim + og * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(sW2 + k * kEmbDim + og * 8 + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const float x = sh[(fg * 4 + a) * ldh + k];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) acc[a][o] = fmaf(x, w[o], acc[a][o]);
+            for (int nt = 0; nt < 16; ++nt) {
+                const float4 b = fr1[(ks * 16 + nt) * 32 + lane];
+                mma_tf32_16x8x8(h[nt], al, __float_as_uint(b.x), __float_as_uint(b.y));
+                mma_tf32_16x8x8(h[nt], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+                mma_tf32_16x8x8(h[nt], ah, __float_as_uint(b.x), __float_as_uint(b.y));
             }
         }
-        // round to bf16 (the GEMM operand) and take |f|^2 of the ROUNDED values: 16 threads share a frame
+        // ---- layer 2: f = h . W2 + b2; accumulator tile ks of layer 1 is k-tile ks here
+        float o[16][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int f = fg * 4 + a;
-            uint32_t pk[4];
-            float nn = 0.f;
+        for (int nt = 0; nt < 16; ++nt) {
+            const float2 bb = *reinterpret_cast<const float2 *>(sb2 + nt * 8 + 2 * t);
+            o[nt][0] = o[nt][2] = bb.x;
+            o[nt][1] = o[nt][3] = bb.y;
+        }
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                pk[o] = pack_bf16(acc[a][2 * o], acc[a][2 * o + 1]);
-                const float lo = bf16lo_to_f32(pk[o]), hi = bf16hi_to_f32(pk[o]);
-                nn = fmaf(lo, lo, nn);
-                nn = fmaf(hi, hi, nn);
+        for (int ks = 0; ks < 16; ++ks) {
+            // A fragment (g, t) (g+8, t) (g, t+4) (g+8, t+4) of relu(h tile ks): column c of a row sits in lane (g, c / 2),
+            // element c & 1 (rows g) or 2 + (c & 1) (rows g + 8)
+            float c[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[e] = fmaxf(h[ks][e], 0.f);
+            const float l0 = __shfl_sync(0xffffffffu, c[0], src_lo), l1 = __shfl_sync(0xffffffffu, c[1], src_lo);
+            const float l2 = __shfl_sync(0xffffffffu, c[2], src_lo), l3 = __shfl_sync(0xffffffffu, c[3], src_lo);
+            const float u0 = __shfl_sync(0xffffffffu, c[0], src_hi), u1 = __shfl_sync(0xffffffffu, c[1], src_hi);
+            const float u2 = __shfl_sync(0xffffffffu, c[2], src_hi), u3 = __shfl_sync(0xffffffffu, c[3], src_hi);
+            const float xa[4] = {odd ? l1 : l0, odd ? l3 : l2, odd ? u1 : u0, odd ? u3 : u2};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ah[i] = tf32_of(xa[i]);
+                al[i] = tf32_of(xa[i] - __uint_as_float(ah[i]));
             }
 #pragma unroll
-            for (int d = 8; d >= 1; d >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, d);
-            if (f < nf) {
-                *reinterpret_cast<uint4 *>(F + (f0 + f) * kEmbDim + og * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                if (og == 0) norm[f0 + f] = nn;
+            for (int nt = 0; nt < 16; ++nt) {
+                const float4 b = fr2[(ks * 16 + nt) * 32 + lane];
+                mma_tf32_16x8x8(o[nt], al, __float_as_uint(b.x), __float_as_uint(b.y));
+                mma_tf32_16x8x8(o[nt], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+                mma_tf32_16x8x8(o[nt], ah, __float_as_uint(b.x), __float_as_uint(b.y));
             }
+        }
+        // ---- round to bf16 (the GEMM operand), |f|^2 of the ROUNDED values, store
+        float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            const uint32_t p0 = pack_bf16(o[nt][0], o[nt][1]), p1 = pack_bf16(o[nt][2], o[nt][3]);
+            n0 = fmaf(bf16lo_to_f32(p0), bf16lo_to_f32(p0), n0);
+            n0 = fmaf(bf16hi_to_f32(p0), bf16hi_to_f32(p0), n0);
+            n1 = fmaf(bf16lo_to_f32(p1), bf16lo_to_f32(p1), n1);
+            n1 = fmaf(bf16hi_to_f32(p1), bf16hi_to_f32(p1), n1);
+            if (r0 < nf) *reinterpret_cast<uint32_t *>(F + (f0 + r0) * kEmbDim + nt * 8 + 2 * t) = p0;
+            if (r1 < nf) *reinterpret_cast<uint32_t *>(F + (f0 + r1) * kEmbDim + nt * 8 + 2 * t) = p1;
+        }
+        n0 += __shfl_xor_sync(0xffffffffu, n0, 1);
+        n0 += __shfl_xor_sync(0xffffffffu, n0, 2);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, 1);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, 2);
+        if (t == 0) {
+            if (r0 < nf) norm[f0 + r0] = n0;
+            if (r1 < nf) norm[f0 + r1] = n1;
         }
     }
+}
+
+// Host: W [K][128] (row-major, K rows used, padded with zeros to ksteps * 8) -> B fragments of mma.sync m16n8k8 (col-major B:
+// b0 = W[ks*8 + t][nt*8 + g], b1 = W[ks*8 + t + 4][nt*8 + g]) split into TF32 head and tail: {hi0, hi1, lo0, lo1} per lane.
+inline float tf32_round_host(float x) {          // cvt.rna.tf32.f32: nearest, ties away from zero, 10 mantissa bits kept
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & ~0x1fffu;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+inline void pack_tf32x3_fragments(const float *W, int K, int ksteps, float *out) {
+    for (int ks = 0; ks < ksteps; ++ks)
+        for (int nt = 0; nt < kEmbHidden / 8; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                float *dst = out + ((size_t)(ks * 16 + nt) * 32 + lane) * 4;
+                for (int h = 0; h < 2; ++h) {
+                    const int k = ks * 8 + t + 4 * h;
+                    const float w = k < K ? W[(size_t)k * kEmbHidden + n] : 0.f;
+                    const float hi = tf32_round_host(w);
+                    dst[h] = hi;
+                    dst[2 + h] = tf32_round_host(w - hi);
+                }
+            }
 }
 
 // One CTA = one 128 x 128 tile of one pair's cost matrix.  192 threads: warp 0 TMA + MMA issue, warp 1 TMEM
@@ -254,6 +333,15 @@ int align_embed_set_encoder(Ctx *ctx, const float *blob, size_t nfloats) {
         ep->b2 = ep->W2 + (size_t)kEmbHidden * kEmbDim;
     }
     GS_CUDA(cudaMemcpy(ep->W1, blob, want * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> frag(kEncFragFloats);
+    pack_tf32x3_fragments(blob, kEmbIn, kEncTcKs1, frag.data());
+    pack_tf32x3_fragments(blob + (size_t)kEmbIn * kEmbHidden + kEmbHidden, kEmbHidden, kEmbHidden / 8,
+                          frag.data() + (size_t)kEncTcKs1 * 16 * 32 * 4);
+    if (!ep->Wfrag) {
+        GS_CUDA(cudaMalloc((void **)&ep->Wfrag, kEncFragFloats * sizeof(float)));
+        ctx->ws_bytes += kEncFragFloats * sizeof(float);
+    }
+    GS_CUDA(cudaMemcpy(ep->Wfrag, frag.data(), kEncFragFloats * sizeof(float), cudaMemcpyHostToDevice));
     return GS_OK;
 }
 
@@ -261,6 +349,7 @@ void align_embed_destroy(Ctx *ctx) {
     EmbedPath *ep = ctx->embed;
     if (!ep) return;
     if (ep->W1) cudaFree(ep->W1);
+    if (ep->Wfrag) cudaFree(ep->Wfrag);
     if (ep->F) cudaFree(ep->F);
     if (ep->norm) cudaFree(ep->norm);
     if (ep->cm) cudaFree(ep->cm);
@@ -304,9 +393,8 @@ int align_embed_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, 
         if ((rc = grow_dev(ctx, &ep->cm, &ep->cm_floats, (size_t)N * ra * rb)) != GS_OK) return rc;
         cm = ep->cm;
     }
-    const size_t enc_smem = ((size_t)kEmbIn * kEmbHidden + kEmbHidden + (size_t)kEmbHidden * kEmbDim + kEmbDim +
-                             (size_t)kEncFrames * kEmbIn + (size_t)kEncFrames * (kEmbHidden + 4)) * sizeof(float);
-    if ((rc = ensure_dyn_smem(ctx, (const void *)embed_encoder_kernel, enc_smem)) != GS_OK) return rc;
+    const size_t enc_smem = (kEncFragFloats + (size_t)kEncFrames * kEncLdx + 2 * kEmbHidden) * sizeof(float);
+    if ((rc = ensure_dyn_smem(ctx, (const void *)embed_encoder_tc_kernel, enc_smem)) != GS_OK) return rc;
     for (int which = 0; which < 2; ++which) {
         const size_t nfr = which == 0 ? rows_a : rows_b;
         int grid = (int)((nfr + kEncFrames - 1) / kEncFrames < (size_t)ctx->sm_count ? (nfr + kEncFrames - 1) / kEncFrames
@@ -314,9 +402,9 @@ int align_embed_launch(Ctx *ctx, const float *a, const float *b, int N, int Ta, 
         if (grid < 1) grid = 1;
         {
             LaunchScope ls(ctx, K_EMBED, st, 2.0 * nfr * (kEmbIn * kEmbHidden + kEmbHidden * kEmbDim), (double)nfr * (V * Cc * 4 + kEmbDim * 2));
-            embed_encoder_kernel<<<grid, kEncThreads, enc_smem, st>>>(which == 0 ? a : b, V, Cc, nfr, ep->W1, ep->b1, ep->W2, ep->b2,
-                                                              ep->F + (which == 0 ? 0 : rows_a * kEmbDim),
-                                                              ep->norm + (which == 0 ? 0 : rows_a));
+            embed_encoder_tc_kernel<<<grid, kEncTcThreads, enc_smem, st>>>(which == 0 ? a : b, V, Cc, nfr, ep->Wfrag, ep->b1, ep->b2,
+                                                                     ep->F + (which == 0 ? 0 : rows_a * kEmbDim),
+                                                                     ep->norm + (which == 0 ? 0 : rows_a));
         }
         GS_KERNEL_CHECK();
     }
