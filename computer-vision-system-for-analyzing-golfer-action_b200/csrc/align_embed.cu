@@ -255,6 +255,14 @@ embed_cost_kernel(const __grid_constant__ CUtensorMap mapF, const float *__restr
         const int ew = warp & 3, r = ew * 32 + lane;
         const int i = i0 + r;
         const float na = i < ra ? norm[arow + r] : 0.f;
+        // the tile's 128 column norms once, in shared memory (every thread needs all of them: a global load per element
+        // per thread was most of this kernel's epilogue)
+        __shared__ float s_nb[128];
+        {
+            const int e = threadIdx.x - 64;
+            s_nb[e] = j0 + e < rb ? norm[brow + e] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&done, 0);
         tc_fence_after();
         // the operand boxes are dead once the MMAs have completed: stage the fp32 tile there, row stride 129 floats
@@ -266,9 +274,7 @@ embed_cost_kernel(const __grid_constant__ CUtensorMap mapF, const float *__restr
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const int j = j0 + c * 16 + e;
-                const float nb = j < rb ? __ldg(norm + brow + c * 16 + e) : 0.f;
-                const float d2 = fmaf(-2.f, __uint_as_float(v[e]), na + nb);
+                const float d2 = fmaf(-2.f, __uint_as_float(v[e]), na + s_nb[c * 16 + e]);
                 stage[r * lds + c * 16 + e] = sqrtf(fmaxf(d2, 0.f));
             }
         }
