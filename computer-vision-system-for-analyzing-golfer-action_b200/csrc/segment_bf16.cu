@@ -41,7 +41,7 @@ struct Bf16Path {
 
 namespace {
 
-constexpr int kFrontFrames = 16;
+constexpr int kFrontFrames = 15;     // 255 rows: one A row per thread of the 256 (16 frames = 272 rows left a second pass for 16 of them)
 
 // ---- block 0 with the two K = 9 / K = 3 mixes on warp-level tensor cores ---------------------------
 // A CUDA-core form is bound by FMA issue (12 x 2C FMAs per row; 0.15 ms against a 0.054 ms
@@ -51,7 +51,7 @@ constexpr int kFrontFrames = 16;
 //     columns [0,C)  : rows 0-8 = Wg, row 12 = bg          -> Y  = relu(.)
 //     columns [C,2C) : rows 9-11 = Wr, row 12 = br         -> R0 (the block's residual projection)
 // as mma.sync m16n8k8 TF32 with fp32 accumulation (inputs and weights rounded to TF32: 2^-11, below the
-// bf16 rounding of the outputs).  One CTA = kFrontFrames frames = 17 m-tiles of 16 rows; a warp owns a
+// bf16 rounding of the outputs).  One CTA = kFrontFrames frames = 16 m-tiles of 16 rows (255 used); a warp owns a
 // 32-column group (its 16 B-fragment registers never change) and every (8 / groups)-th m-tile.
 constexpr int kFrontLd = 20;     // A-row stride in floats: conflict-free fragment loads
 
@@ -80,7 +80,7 @@ front_mma_kernel(const float *__restrict__ skel, const float *__restrict__ in_sc
     float *sA = sm;                                    // [3][17][17] adjacency
     float *sx = sA + 3 * V17 * V17 + 1;                // [rows][CIN] normalised input
     uint32_t *sam = reinterpret_cast<uint32_t *>(sx + kFrontFrames * V17 * CIN);   // [rows][kFrontLd] tf32 A rows
-    constexpr int kRows = kFrontFrames * V17;          // 272 = 17 m-tiles
+    constexpr int kRows = (kFrontFrames * V17 + 15) / 16 * 16;     // 256 = 16 m-tiles, row 255 is padding
     for (int k = threadIdx.x; k < 3 * V17 * V17; k += blockDim.x) sA[k] = A[k];
     const size_t f0 = (size_t)blockIdx.x * kFrontFrames;
     const int nf = (int)(nframes - f0 < (size_t)kFrontFrames ? nframes - f0 : (size_t)kFrontFrames);
@@ -456,7 +456,7 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
         bf *U = (bf *)ctx->bufU[i & 1];
         const bool proj = (i > 0 && b.has_res);
         if (i == 0) {
-            const size_t smem = ((size_t)3 * V17 * V17 + 1 + (size_t)kFrontFrames * V17 * (cin + kFrontLd)) * sizeof(float);
+            const size_t smem = ((size_t)3 * V17 * V17 + 1 + (size_t)kFrontFrames * V17 * cin + (size_t)((kFrontFrames * V17 + 15) / 16 * 16) * kFrontLd) * sizeof(float);
             // one launch, or one per input chunk of gs_segment_host (whole clips: both output layouts are per clip)
             const int nch = ctx->front_nchunks > 0 ? ctx->front_nchunks : 1;
             for (int k = 0; k < nch; ++k) {
