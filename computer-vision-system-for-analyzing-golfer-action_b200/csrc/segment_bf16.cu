@@ -30,6 +30,7 @@ struct Bf16Path {
     std::vector<__nv_bfloat16 *> Bt1, Bt2;              // bias tiles [C][16] of the temporal kernel: b1; b2 (+ br)
     std::vector<float *> stjP[3];                       // ST-joint {W, Wt, Wv} in fp16 fragment order (stj_tc_kernel)
     std::vector<std::vector<float>> bgHost;             // host copies of the GCN biases: they travel as kernel parameters (gcn_fused.cuh)
+    std::vector<std::vector<float>> b1Host, b2Host;     // temporal kernel at C = 256: b1 and b2 (+ br) as kernel parameters (tcn_fused.cuh)
     float *frontB = nullptr;                            // block 0: [16][2C] TF32 matrix of front_mma_kernel
     __nv_bfloat16 *ident64 = nullptr;                   // 64x64 identity: "projection" weights of the identity residual (tcn_fused.cuh)
     std::vector<BlockMaps> maps;
@@ -379,6 +380,10 @@ int bf16_path_create(Ctx *ctx) {
         };
         if ((rc = bias_tile(host(b.b1), &bp->Bt1[i]))) return rc;
         if ((rc = bias_tile(bias.data(), &bp->Bt2[i]))) return rc;
+        bp->b1Host.resize(nb);
+        bp->b2Host.resize(nb);
+        bp->b1Host[i].assign(host(b.b1), host(b.b1) + C);
+        bp->b2Host[i] = bias;
         if (i == 0) {   // block 0 on warp-level tensor cores (front_mma_kernel)
             std::vector<float> bm;
             pack_front_matrix(host(b.Wg), host(b.bg), host(b.Wr), host(b.br), C, bm);
@@ -509,6 +514,10 @@ int segment_bf16_forward(Ctx *ctx, const float *skel, float *logits, uint8_t *la
             tf::Params &q = L.prm;
             memset(&q, 0, sizeof(q));
             q.B = B; q.T = T; q.C = C; q.cr = cr; q.cin = cin;
+            if (cr >= 64 && C <= 256) {
+                memcpy(q.b1v, bp->b1Host[i].data(), (size_t)C * sizeof(float));
+                memcpy(q.b2v, bp->b2Host[i].data(), (size_t)C * sizeof(float));
+            }
             q.nbr = 64 / cr;
             q.res_q = proj ? 0 : 1;
             q.nkx = proj ? cin / 64 : 1;

@@ -75,6 +75,7 @@ struct Params {
     uint32_t w1_off, w2_off, wr_off, w1_bytes, w2_bytes, wr_bytes, bias_off, hbox_off, hbox_span, out_off, scr_off, bar_off, total;
     float *PT;            // [B,T,C]
     float *PVpart;        // [B,ttiles,17,C]
+    float b1v[256], b2v[256];   // CR = 64 (C = 256) only: the two biases by value, added in registers from the constant bank
     unsigned long long *trace;   // optional clock64 trace of CTA 0 (GOLFER_TRACE_TCN=1, tools/trace_tcn.py)
 };
 
@@ -148,6 +149,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
     const int T = prm.T, nout = prm.nout;
     constexpr int NBR = 64 / CR;
     constexpr int CRM = CR < 16 ? 16 : CR;          // MMA width (K and N) per branch tap
+    constexpr bool kBiasRegs = (CR >= 64);          // C = 256: biases added in registers instead of through the tensor core
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.y_win);
@@ -293,7 +295,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             mbar_wait(&hempty[hb], ((n >> 1) & 1u) ^ 1u);
             if (lane == 0) TF_TRACE(2, n, 1);
             tc_fence_after();
-            if (elect_one()) umma_bf16(th, d_ones, d_b1, idesc_64, 0u);     // Hacc = b1
+            if (!kBiasRegs && elect_one()) umma_bf16(th, d_ones, d_b1, idesc_64, 0u);     // Hacc = b1
             for (int kb = 0; kb < prm.nky; ++kb) {
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
@@ -301,7 +303,9 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 const uint64_t db = d_w1 + (uint64_t)((uint32_t)kb * (8192u >> 4));
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(th, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64,
+                                  kBiasRegs ? (uint32_t)((kb > 0) | (k > 0)) : 1u);
                     umma_commit(&empty[slot]);
                 }
                 __syncwarp();
@@ -318,7 +322,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (lane == 0) TF_TRACE(2, n, 5);
             tc_fence_after();
             const uint32_t td = tmem_base + buf * 64u;
-            if (elect_one()) umma_bf16(td, d_ones, d_b2, idesc_64, 0u);     // U = b2 (+ projection bias)
+            if (!kBiasRegs && elect_one()) umma_bf16(td, d_ones, d_b2, idesc_64, 0u);     // U = b2 (+ projection bias)
             for (int kx = 0; kx < prm.nkx; ++kx) {
                 mbar_wait(&full[slot], phase);
                 tc_fence_after();
@@ -326,7 +330,9 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 const uint64_t db = d_wr + (uint64_t)((uint32_t)kx * (8192u >> 4));
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64, 1u);
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_64,
+                                  kBiasRegs ? (uint32_t)((kx > 0) | (k > 0)) : 1u);
                     umma_commit(&empty[slot]);
                 }
                 __syncwarp();
@@ -363,6 +369,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
         // accumulator slices fetched up front.
         const int ew = warp & 3;                             // TMEM lane quarter this warp may access
         const int cq = (warp - 2) >> 2;                      // 16-column quarter of the box
+        const float *b1q = prm.b1v + q * 64 + cq * 16, *b2q = prm.b2v + q * 64 + cq * 16;   // kBiasRegs: constant bank
         const int gt = threadIdx.x - 64;                     // 0..511
         const int r = ew * 32 + lane;                        // row inside the tile
         const bool leader = (gt == 0);
@@ -437,6 +444,13 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
             if (do_cv) {
                 // ---- convert(n): Hacc (b1 included) -> ReLU + bf16 in one conversion, zero outside [0,T) -> K-major Hbox
                 uint4 p0, p1;
+                if (kBiasRegs) {
+                    // C = 256: the kernel sits at the shared-memory pipe, and the bias MMAs read 12 KB of operands per
+                    // step through it; here the biases come from the constant bank (warp-uniform index: no register,
+                    // no shared-memory load) and cost 32 FADDs per thread and step in warps that have the slack
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acch[e] = __float_as_uint(__uint_as_float(acch[e]) + b1q[e]);
+                }
                 p0.x = pack_bf16_relu(__uint_as_float(acch[0]), __uint_as_float(acch[1]));
                 p0.y = pack_bf16_relu(__uint_as_float(acch[2]), __uint_as_float(acch[3]));
                 p0.z = pack_bf16_relu(__uint_as_float(acch[4]), __uint_as_float(acch[5]));
@@ -470,7 +484,7 @@ tcn_fused_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Para
                 float f[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    f[e] = fmaxf(__uint_as_float(accu[e]), 0.f);
+                    f[e] = fmaxf(kBiasRegs ? __uint_as_float(accu[e]) + b2q[e] : __uint_as_float(accu[e]), 0.f);
                     // frame pooling (sum over joints) of the fp32 values, as the oracle pools (the stored copy is
                     // their bf16 rounding)
                     pt[e] += f[e];
