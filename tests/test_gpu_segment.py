@@ -191,11 +191,12 @@ def test_bf16_stress_config_eight_branches(B, T):
     seg.ctx.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_host_entry_point_equals_device_entry_point(prec):
+@pytest.mark.parametrize("prec,B", [("fp32", 16), ("bf16", 16), ("bf16", 19), ("bf16", 5)])
+def test_host_entry_point_equals_device_entry_point(prec, B):
+    # bf16: the input goes up in 4 chunks of whole clips when B >= 16 (19 = 5 + 5 + 5 + 4), in one otherwise
     cfg = golfer_b200.V0
-    seg = golfer_b200.Segmenter(cfg, precision=prec, max_B=16, max_T=40)
-    skel = osegnet.synth_skeletons(16, 40, cfg, seed=2)
+    seg = golfer_b200.Segmenter(cfg, precision=prec, max_B=B, max_T=40)
+    skel = osegnet.synth_skeletons(B, 40, cfg, seed=2)
     dev = seg.segment(torch.from_numpy(skel).cuda()).cpu().numpy()
     host_logits, host_labels = seg.segment(skel, return_labels=True)     # numpy in -> numpy out
     assert isinstance(host_logits, np.ndarray)
