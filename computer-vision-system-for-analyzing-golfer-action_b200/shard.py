@@ -54,6 +54,39 @@ def gather_shards(local, n_total: int, dist=None, group=None):
     return torch.cat([out[r * biggest:r * biggest + sizes[r]] for r in range(world)], 0)
 
 
+class OverlappedGather:
+    """`gather_shards` on a side stream, for a loop of independent batches: the collective of batch n runs under the
+    kernels of batch n+1 instead of between them (the gather is ~0.1 ms of launch and synchronisation latency per
+    batch whatever its size, 3 % of a 4 ms step on 8 GPUs).  `submit` returns the gathered tensor at once; it is valid
+    on the CURRENT stream only after `wait()`.  Without an initialised process group, or for host tensors (the gloo
+    tests), it degrades to the synchronous `gather_shards`."""
+
+    def __init__(self, dist=None, group=None):
+        self.dist, self.group, self.stream = dist, group, None
+
+    def submit(self, local, n_total: int):
+        import torch
+
+        dist = self.dist
+        if dist is None:
+            import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or not local.is_cuda:
+            return gather_shards(local, n_total, dist, self.group)
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(local.device)
+        self.stream.wait_stream(torch.cuda.current_stream(local.device))      # behind the kernels that produced `local`
+        with torch.cuda.stream(self.stream):
+            out = gather_shards(local, n_total, dist, self.group)
+        local.record_stream(self.stream)          # the allocator must not hand `local` out again while the collective reads it
+        return out
+
+    def wait(self):
+        import torch
+
+        if self.stream is not None:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+
+
 def run_sharded(fn: Callable, inputs: Sequence, n_total: Optional[int] = None, dist=None, group=None):
     """Apply `fn(*shards)` to this rank's contiguous shard of every input (dim 0 = units) and
     gather every output.  `fn` returns a tensor or a tuple of tensors whose dim 0 is the shard."""

@@ -40,10 +40,17 @@ def main():
 
     got_logits, got_labels = run_sharded(seg_fn, [skel], dist=dist)
     got_cost, got_path, got_plen = run_sharded(al_fn, [a, b], dist=dist)
+    # the overlapped form bench.py uses: the collectives on a side stream, valid after wait()
+    from golfer_b200.shard import OverlappedGather, shard_range
+    og = OverlappedGather(dist)
+    lo, hi = shard_range(B, dist.get_rank(), world)
+    ov = [og.submit(seg_fn(skel[lo:hi])[1], B) for _ in range(3)]     # three batches in a row, no wait in between
+    og.wait()
     want_logits, want_labels = seg_fn(skel)
     want_cost, want_path, want_plen = al_fn(a, b)
     torch.cuda.synchronize()
     ok = (torch.equal(got_logits, want_logits) and torch.equal(got_labels, want_labels)
+          and all(torch.equal(o, want_labels) for o in ov)
           and torch.equal(got_cost, want_cost) and torch.equal(got_path, want_path) and torch.equal(got_plen, want_plen))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
