@@ -646,9 +646,12 @@ def main():
         def al_step():
             cost, path, plen = golfer_b200.host.align_batch(a, b, ctx=actx)
             if dist is not None:       # int16 halves the only sizeable collective of the job (frame indices < 32768)
-                gatherer.submit(path.to(torch.int16), world * N)      # side stream: under the next step's sweep
-                gatherer.submit(plen, world * N)
-                gatherer.submit(cost, world * N)
+                # in-stream on purpose: on a side stream (shard.OverlappedGather) the 78 MB collective of 8 ranks shares
+                # the SMs with the next step's persistent sweep and the ranks wait for each other inside it:
+                # 12.8 ms per step instead of 4.2 (measured at N = 8; at N = 2 it was the faster form)
+                gather_shards(path.to(torch.int16), world * N, dist)
+                gather_shards(plen, world * N, dist)
+                gather_shards(cost, world * N, dist)
             return cost
 
         for _ in range(W):
@@ -660,7 +663,6 @@ def main():
         e0.record()
         for _ in range(K):
             al_step()
-        gatherer.wait()
         e1.record()
         barrier()
         actx.profile(False)
