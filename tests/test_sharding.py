@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import golfer_b200
-from golfer_b200.shard import gather_shards, run_sharded, shard_range, shard_sizes
+from golfer_b200.shard import OverlappedGather, gather_shards, run_sharded, shard_range, shard_sizes
 
 
 def test_shard_ranges_partition_in_order():
@@ -32,6 +32,9 @@ def test_shard_ranges_partition_in_order():
 def test_without_process_group_is_identity():
     x = torch.arange(12.).reshape(6, 2)
     assert torch.equal(gather_shards(x, 6), x)
+    og = OverlappedGather()
+    assert torch.equal(og.submit(x, 6), x)
+    og.wait()
     assert torch.equal(run_sharded(lambda a: a * 2, [x]), x * 2)
 
 
@@ -69,6 +72,12 @@ def _worker(rank, world, port, n_clips, n_pairs, out_dir):
         _, path16, _ = run_sharded(lambda x, y: tuple(t.to(torch.int16) if t.dtype == torch.int32 and t.dim() == 3 else t
                                                       for t in align_fn(x, y)), [a, b])
         assert path16.dtype == torch.int16 and torch.equal(path16.to(torch.int32), path)
+        # the overlapped form of the gather (a side stream on GPUs) degrades to the synchronous one for host tensors
+        og = OverlappedGather(dist)
+        lo, hi = shard_range(n_clips, rank, world)
+        ov = og.submit(seg_fn(skel[lo:hi]), n_clips)
+        og.wait()
+        assert torch.equal(ov, logits)
         if rank == 0:
             np.savez(os.path.join(out_dir, f"gathered_w{world}.npz"), logits=logits.numpy(), cost=cost.numpy(),
                      path=path.numpy(), plen=plen.numpy())
